@@ -1,0 +1,213 @@
+"""ctypes binding of the C ABI in include/msda.h (the thin layer north_star asks for).
+
+This is the ONLY route from Python to the kernels.  There is no CPU or pure-PyTorch fallback: if
+``libmsda_b200.so`` is missing the import of anything that needs it raises, and CPU tensors are
+rejected the way the reference rejects them (models/ops/src/ms_deform_attn.h:38,60).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+MSDA_F32, MSDA_F64, MSDA_BF16 = 0, 1, 2
+FLAG_ZERO_GRAD_VALUE = 1 << 0
+FLAG_DETERMINISTIC = 1 << 1
+FLAG_FORCE_GENERIC = 1 << 2
+
+_DTYPE_CODE = {torch.float32: MSDA_F32, torch.float64: MSDA_F64, torch.bfloat16: MSDA_BF16}
+
+
+class MsdaDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int64) for n in
+                ("batch", "spatial_size", "num_heads", "channels", "num_levels", "num_query", "num_point")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen the CUDA library; raise loudly when it is absent (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"{path} is missing: the sm_100a CUDA library has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'` or `python -m grit_b200.build`). "
+                "grit_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(path)
+        vp, i64p, dimsp = ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(MsdaDims)
+        lib.msda_abi_version.restype = ctypes.c_int
+        lib.msda_last_error.restype = ctypes.c_char_p
+        lib.msda_last_kernel.restype = ctypes.c_char_p
+        lib.msda_launch_count.restype = ctypes.c_int64
+        lib.msda_launch_count.argtypes = [ctypes.c_int]
+        lib.msda_forward.restype = ctypes.c_int
+        lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint, vp]
+        lib.msda_backward_workspace_bytes.restype = ctypes.c_size_t
+        lib.msda_backward_workspace_bytes.argtypes = [dimsp, ctypes.c_int, ctypes.c_uint]
+        lib.msda_backward.restype = ctypes.c_int
+        lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint,
+                                      vp, ctypes.c_size_t, vp]
+        lib.msda_host_session_create.restype = ctypes.c_int
+        lib.msda_host_session_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), dimsp, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int]
+        lib.msda_host_session_destroy.restype = None
+        lib.msda_host_session_destroy.argtypes = [vp]
+        lib.msda_host_forward_backward.restype = ctypes.c_int
+        lib.msda_host_forward_backward.argtypes = [vp, vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, dimsp,
+                                                   ctypes.c_uint]
+        if lib.msda_abi_version() != 1:
+            raise RuntimeError(f"{path}: ABI version {lib.msda_abi_version()} != 1")
+        _lib = lib
+    return _lib
+
+
+def last_kernel() -> str:
+    return load().msda_last_kernel().decode()
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().msda_launch_count(1 if reset else 0))
+
+
+def _raise(lib, rc, what):
+    raise RuntimeError(f"{what} failed (code {rc}): {lib.msda_last_error().decode()}")
+
+
+def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output=None):
+    """The reference's host-side preconditions (ms_deform_attn_cuda.cu:28-38, 93-105; ms_deform_attn.h:38,60)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", sampling_loc), ("attn_weight", attn_weight)]
+    if grad_output is not None:
+        named.append(("grad_output", grad_output))
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+        if t.device != value.device:
+            raise RuntimeError(f"{name} is on {t.device}, value is on {value.device}")
+    if value.dtype not in _DTYPE_CODE:
+        raise RuntimeError(f'"ms_deform_attn" not implemented for \'{value.dtype}\'')
+    loc_dtype = torch.float64 if value.dtype == torch.float64 else torch.float32
+    for name, t in (("sampling_loc", sampling_loc), ("attn_weight", attn_weight)):
+        if t.dtype != loc_dtype:
+            raise RuntimeError(f"expected {name} of dtype {loc_dtype} for value of dtype {value.dtype}, "
+                               f"but found {t.dtype}")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64 (torch.long) tensors")
+    if grad_output is not None and grad_output.dtype != value.dtype:
+        raise RuntimeError(f"grad_output dtype {grad_output.dtype} does not match value dtype {value.dtype}")
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5 or sampling_loc.shape[-1] != 2:
+        raise RuntimeError("expected value (N,S,M,D), sampling_loc (N,Lq,M,L,P,2), attn_weight (N,Lq,M,L,P)")
+    n, s, m, d = value.shape
+    n2, lq, m2, l, p, _ = sampling_loc.shape
+    if (n2, m2) != (n, m) or tuple(attn_weight.shape) != (n, lq, m, l, p):
+        raise RuntimeError("value / sampling_loc / attn_weight shapes disagree")
+    if tuple(spatial_shapes.shape) != (l, 2) or level_start_index.numel() != l:
+        raise RuntimeError("spatial_shapes must be (L,2) and level_start_index (L,) with L = sampling_loc.size(3)")
+    return MsdaDims(n, s, m, d, l, lq, p)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, flags: int = 0):
+    """-> output (N, Lq, M*D).  Mirrors ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80)."""
+    lib = load()
+    dims = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
+                      device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+                              _ptr(attn_weight), _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], flags,
+                              ctypes.c_void_p(stream))
+    if rc:
+        _raise(lib, rc, "msda_forward")
+    return out
+
+
+def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, flags: int = 0):
+    """-> (grad_value, grad_sampling_loc, grad_attn_weight).  Mirrors ms_deform_attn_cuda_backward (:83-153)."""
+    lib = load()
+    dims = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output)
+    code = _DTYPE_CODE[value.dtype]
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags)
+    if code == MSDA_BF16:
+        grad_value = torch.empty_like(value)
+        flags |= FLAG_ZERO_GRAD_VALUE  # the fold kernel then overwrites instead of accumulating
+    else:
+        grad_value = torch.zeros_like(value)
+    workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = lib.msda_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+                               _ptr(attn_weight), _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc),
+                               _ptr(grad_attn), ctypes.byref(dims), code, flags,
+                               _ptr(workspace) if workspace is not None else None, ws_bytes,
+                               ctypes.c_void_p(stream))
+    if rc:
+        _raise(lib, rc, "msda_backward")
+    return grad_value, grad_loc, grad_attn
+
+
+class HostSession:
+    """Host-buffer forward+backward (include/msda.h: msda_host_session); bench.py's e2e leg."""
+
+    def __init__(self, max_dims: MsdaDims, dtype: torch.dtype, device: int = 0, images_per_chunk: int = 1):
+        self._lib = load()
+        self._handle = ctypes.c_void_p()
+        self.dtype = dtype
+        rc = self._lib.msda_host_session_create(ctypes.byref(self._handle), ctypes.byref(max_dims),
+                                                _DTYPE_CODE[dtype], device, images_per_chunk)
+        if rc:
+            _raise(self._lib, rc, "msda_host_session_create")
+
+    def forward_backward(self, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                         output, grad_value, grad_loc, grad_attn, flags: int = 0):
+        """All arguments are HOST tensors (ideally pinned); outputs are written in place."""
+        for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, output,
+                  grad_value, grad_loc, grad_attn):
+            if t.is_cuda or not t.is_contiguous():
+                raise RuntimeError("HostSession expects contiguous host tensors")
+        n, s, m, d = value.shape
+        _, lq, _, l, p, _ = sampling_loc.shape
+        dims = MsdaDims(n, s, m, d, l, lq, p)
+        rc = self._lib.msda_host_forward_backward(
+            self._handle, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+            _ptr(attn_weight), _ptr(grad_output), _ptr(output), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
+            ctypes.byref(dims), flags)
+        if rc:
+            _raise(self._lib, rc, "msda_host_forward_backward")
+
+    def close(self):
+        if self._handle:
+            self._lib.msda_host_session_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

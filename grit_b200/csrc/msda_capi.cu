@@ -1,0 +1,473 @@
+// msda_capi.cu -- host side of the C ABI declared in include/msda.h.
+//
+// Replaces the reference's host launchers (models/ops/src/cuda/ms_deform_attn_cuda.cu:20-153 and
+// ms_deform_im2col_cuda.cuh:923-1327): argument checks, kernel selection by (dtype, D, L, P),
+// launch on the caller's stream, errors returned instead of printed.  No device allocation, no
+// synchronisation, no host read of spatial_shapes.
+#include "../../include/msda.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_kernels.cuh"
+
+namespace {
+
+thread_local char tl_error[512] = "";
+thread_local char tl_kernel[128] = "";
+thread_local int64_t tl_launches = 0;
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return MSDA_OK;
+    return fail(MSDA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+const char *dtype_name(int dtype)
+{
+    return dtype == MSDA_F32 ? "f32" : dtype == MSDA_F64 ? "f64" : dtype == MSDA_BF16 ? "bf16" : "?";
+}
+
+size_t dtype_size(int dtype) { return dtype == MSDA_F32 ? 4 : dtype == MSDA_F64 ? 8 : 2; }
+
+int check_dims(const msda_dims *d, int dtype)
+{
+    if (!d) return fail(MSDA_ERR_INVALID_ARGUMENT, "dims is null");
+    if (dtype != MSDA_F32 && dtype != MSDA_F64 && dtype != MSDA_BF16)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (d->batch < 0 || d->num_query < 0 || d->spatial_size < 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "negative batch/num_query/spatial_size");
+    if (d->num_heads <= 0 || d->channels <= 0 || d->num_levels <= 0 || d->num_point <= 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "num_heads, channels, num_levels, num_point must be positive");
+    if (d->num_levels > 1024 || d->num_point > (1 << 20) || d->channels > (1 << 24) || d->num_heads > (1 << 20))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "dimension out of range");
+    // per-image element count must fit 31 bits (64-bit image bases are used on top of it)
+    const int64_t per_image = d->spatial_size * d->num_heads * d->channels;
+    if (d->spatial_size > 0 && per_image / d->spatial_size != d->num_heads * d->channels)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "per-image size overflows");
+    if (d->batch * d->num_query * d->num_heads > ((int64_t)1 << 40))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "batch*num_query*num_heads too large");
+    return MSDA_OK;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kWarps = 8;
+
+struct Geometry {
+    int64_t rows;
+    unsigned grid;
+};
+
+int geometry(const msda_dims *d, Geometry *g)
+{
+    g->rows = d->batch * d->num_query * d->num_heads;
+    const int64_t blocks = (g->rows + kWarps - 1) / kWarps;
+    if (blocks > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
+    g->grid = (unsigned)blocks;
+    return MSDA_OK;
+}
+
+bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
+{
+    if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
+    if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+    return d->spatial_size * d->num_heads * d->channels < ((int64_t)1 << 31);
+}
+
+// ---- specialisation tables -----------------------------------------------------------------------
+#define MSDA_FOR_EACH_SPEC(X) \
+    X(32, 4, 4)               \
+    X(64, 4, 4)               \
+    X(16, 4, 4)               \
+    X(128, 4, 4)              \
+    X(32, 4, 8)               \
+    X(64, 4, 8)               \
+    X(32, 1, 4)               \
+    X(64, 1, 4)               \
+    X(32, 1, 8)               \
+    X(64, 1, 8)
+
+template <typename T>
+const char *tname();
+template <>
+const char *tname<float>() { return "f32"; }
+template <>
+const char *tname<__nv_bfloat16>() { return "bf16"; }
+
+template <typename T>
+bool launch_fwd_vec(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                    const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+#define X(DD, LL, PP)                                                                                          \
+    if constexpr ((DD) % E == 0 && 32 % ((DD) / E) == 0 && ((LL) * (PP)) % (32 / ((DD) / E)) == 0) {          \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                           \
+            msda::msda_fwd_vec<T, DD, LL, PP, kWarps><<<g.grid, kWarps * 32, 0, st>>>(                        \
+                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out,             \
+                (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, g.rows);                          \
+            snprintf(tl_kernel, sizeof(tl_kernel), "fwd_vec<%s,D%d,L%d,P%d>", tname<T>(), DD, LL, PP);        \
+            return true;                                                                                       \
+        }                                                                                                      \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+    return false;
+}
+
+template <typename T>
+bool launch_bwd_vec(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                    const int64_t *lsi, const void *loc, const void *attn, const void *gout, float *gv_acc,
+                    void *gloc, void *gattn, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+#define X(DD, LL, PP)                                                                                          \
+    if constexpr ((DD) % E == 0 && 32 % ((DD) / E) == 0 && ((LL) * (PP)) % (32 / ((DD) / E)) == 0 &&          \
+                  ((LL) * (PP)) / (32 / ((DD) / E)) <= (DD) / E) {                                             \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                           \
+            msda::msda_bwd_vec<T, DD, LL, PP, kWarps><<<g.grid, kWarps * 32, 0, st>>>(                        \
+                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout,      \
+                gv_acc, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads,               \
+                (int)d->num_query, g.rows);                                                                    \
+            snprintf(tl_kernel, sizeof(tl_kernel), "bwd_vec<%s,D%d,L%d,P%d>", tname<T>(), DD, LL, PP);        \
+            return true;                                                                                       \
+        }                                                                                                      \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+    return false;
+}
+
+template <typename T, typename C>
+void launch_fwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                        const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st,
+                        const char *name)
+{
+    const size_t smem = 3 * sizeof(int) * (size_t)d->num_levels;
+    msda::msda_fwd_generic<T, C, kWarps><<<g.grid, kWarps * 32, smem, st>>>(
+        (const T *)value, shapes, lsi, (const C *)loc, (const C *)attn, (T *)out, d->spatial_size,
+        (int)d->num_heads, (int)d->channels, (int)d->num_levels, d->num_query, (int)d->num_point, g.rows);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_generic<%s>", name);
+}
+
+template <typename T, typename C>
+void launch_bwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                        const int64_t *lsi, const void *loc, const void *attn, const void *gout, void *gv_acc,
+                        void *gloc, void *gattn, cudaStream_t st, const char *name)
+{
+    const size_t smem = 3 * sizeof(int) * (size_t)d->num_levels;
+    msda::msda_bwd_generic<T, C, kWarps><<<g.grid, kWarps * 32, smem, st>>>(
+        (const T *)value, shapes, lsi, (const C *)loc, (const C *)attn, (const T *)gout, (C *)gv_acc, (C *)gloc,
+        (C *)gattn, d->spatial_size, (int)d->num_heads, (int)d->channels, (int)d->num_levels, d->num_query,
+        (int)d->num_point, g.rows);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_generic<%s>", name);
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_abi_version(void) { return MSDA_ABI_VERSION; }
+
+const char *msda_last_error(void) { return tl_error; }
+
+const char *msda_last_kernel(void) { return tl_kernel; }
+
+int64_t msda_launch_count(int reset)
+{
+    const int64_t n = tl_launches;
+    if (reset) tl_launches = 0;
+    return n;
+}
+
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims, int dtype,
+                 unsigned flags, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (int rc = check_dims(dims, dtype)) return rc;
+    Geometry g;
+    if (int rc = geometry(dims, &g)) return rc;
+    if (g.rows == 0) return MSDA_OK;  // nothing to write: output has zero elements
+    if (!value && dims->spatial_size > 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "value is null");
+    if (!spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+
+    bool done = false;
+    if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
+        (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
+        if (dtype == MSDA_F32)
+            done = launch_fwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         output, st);
+        else
+            done = launch_fwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, output, st);
+    }
+    if (!done) {
+        if (dtype == MSDA_F32)
+            launch_fwd_generic<float, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                             attn_weight, output, st, "f32");
+        else if (dtype == MSDA_F64)
+            launch_fwd_generic<double, double>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                               attn_weight, output, st, "f64");
+        else
+            launch_fwd_generic<__nv_bfloat16, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                                     attn_weight, output, st, "bf16");
+    }
+    ++tl_launches;
+    return check_cuda(cudaPeekAtLastError(), "msda_forward launch");
+}
+
+size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags)
+{
+    (void)flags;
+    if (!dims) return 0;
+    if (dtype == MSDA_BF16)  // fp32 accumulation image of grad_value
+        return (size_t)(dims->batch * dims->spatial_size * dims->num_heads * dims->channels) * sizeof(float);
+    return 0;
+}
+
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
+                  void *grad_sampling_loc, void *grad_attn_weight, const msda_dims *dims, int dtype, unsigned flags,
+                  void *workspace, size_t workspace_bytes, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (int rc = check_dims(dims, dtype)) return rc;
+    if (flags & MSDA_FLAG_DETERMINISTIC)
+        return fail(MSDA_ERR_UNSUPPORTED, "deterministic backward is not built into this version");
+    Geometry g;
+    if (int rc = geometry(dims, &g)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+
+    if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
+    if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && dtype != MSDA_BF16)
+        if (int rc = check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * dtype_size(dtype), st),
+                                "memset grad_value"))
+            return rc;
+    if (g.rows == 0) {
+        if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && dtype == MSDA_BF16)
+            return check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * 2, st), "memset grad_value");
+        return MSDA_OK;
+    }
+    if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
+        !grad_sampling_loc || !grad_attn_weight)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+
+    void *gv_acc = grad_value;
+    if (dtype == MSDA_BF16) {
+        const size_t need = msda_backward_workspace_bytes(dims, dtype, flags);
+        if (!workspace || workspace_bytes < need)
+            return fail(MSDA_ERR_WORKSPACE, "bf16 backward needs a %zu-byte workspace, got %zu", need,
+                        workspace_bytes);
+        if (!aligned16(workspace)) return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+        if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, need, st), "memset workspace")) return rc;
+        gv_acc = workspace;
+    }
+
+    bool done = false;
+    if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) && aligned16(gv_acc) &&
+        (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
+        (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0) {
+        if (dtype == MSDA_F32)
+            done = launch_bwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                         grad_output, (float *)gv_acc, grad_sampling_loc, grad_attn_weight, st);
+        else
+            done = launch_bwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                                 attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                 grad_attn_weight, st);
+    }
+    if (!done) {
+        if (dtype == MSDA_F32)
+            launch_bwd_generic<float, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                             attn_weight, grad_output, gv_acc, grad_sampling_loc, grad_attn_weight,
+                                             st, "f32");
+        else if (dtype == MSDA_F64)
+            launch_bwd_generic<double, double>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                               attn_weight, grad_output, gv_acc, grad_sampling_loc, grad_attn_weight,
+                                               st, "f64");
+        else
+            launch_bwd_generic<__nv_bfloat16, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                                     attn_weight, grad_output, gv_acc, grad_sampling_loc,
+                                                     grad_attn_weight, st, "bf16");
+    }
+    ++tl_launches;
+    if (int rc = check_cuda(cudaPeekAtLastError(), "msda_backward launch")) return rc;
+
+    if (dtype == MSDA_BF16) {
+        const int threads = 256;
+        int64_t blocks = (n_value / 8 + threads - 1) / threads;
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
+            (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value,
+            (flags & MSDA_FLAG_ZERO_GRAD_VALUE) ? 0 : 1);
+        ++tl_launches;
+        if (int rc = check_cuda(cudaPeekAtLastError(), "msda_fold_workspace_bf16 launch")) return rc;
+    }
+    return MSDA_OK;
+}
+
+// ---- host-buffer session ---------------------------------------------------------------------------
+
+struct msda_host_session {
+    static constexpr int kSlots = 3;
+    msda_dims max_dims;
+    int dtype;
+    int device;
+    int chunk;  // images per chunk
+    int64_t *d_shapes, *d_lsi;
+    cudaStream_t stream[kSlots];
+    struct Slot {
+        char *value, *loc, *attn, *gout, *out, *gvalue, *gloc, *gattn, *ws;
+    } slot[kSlots];
+    size_t ws_bytes;
+};
+
+static void session_free(msda_host_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (int i = 0; i < msda_host_session::kSlots; ++i) {
+        if (s->stream[i]) cudaStreamDestroy(s->stream[i]);
+        char *ptrs[] = {s->slot[i].value, s->slot[i].loc,    s->slot[i].attn, s->slot[i].gout, s->slot[i].out,
+                        s->slot[i].gvalue, s->slot[i].gloc,  s->slot[i].gattn, s->slot[i].ws};
+        for (char *p : ptrs)
+            if (p) cudaFree(p);
+    }
+    if (s->d_shapes) cudaFree(s->d_shapes);
+    if (s->d_lsi) cudaFree(s->d_lsi);
+    delete s;
+}
+
+int msda_host_session_create(msda_host_session **session, const msda_dims *max_dims, int dtype, int device,
+                             int images_per_chunk)
+{
+    tl_error[0] = 0;
+    if (!session) return fail(MSDA_ERR_INVALID_ARGUMENT, "session out-pointer is null");
+    *session = nullptr;
+    if (int rc = check_dims(max_dims, dtype)) return rc;
+    if (images_per_chunk <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "images_per_chunk must be positive");
+    if (int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return rc;
+    auto *s = new msda_host_session();
+    memset(s, 0, sizeof(*s));
+    s->max_dims = *max_dims;
+    s->dtype = dtype;
+    s->device = device;
+    s->chunk = images_per_chunk;
+    const size_t ev = dtype_size(dtype), el = dtype == MSDA_F64 ? 8 : 4;
+    const msda_dims &d = *max_dims;
+    const size_t c = (size_t)images_per_chunk;
+    const size_t n_val = c * d.spatial_size * d.num_heads * d.channels;
+    const size_t n_pts = c * d.num_query * d.num_heads * d.num_levels * d.num_point;
+    const size_t n_out = c * d.num_query * d.num_heads * d.channels;
+    msda_dims cd = d;
+    cd.batch = images_per_chunk;
+    s->ws_bytes = msda_backward_workspace_bytes(&cd, dtype, 0);
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](char **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc((void **)p, bytes ? bytes : 16);
+    };
+    alloc((char **)&s->d_shapes, sizeof(int64_t) * 2 * d.num_levels);
+    alloc((char **)&s->d_lsi, sizeof(int64_t) * d.num_levels);
+    for (int i = 0; i < msda_host_session::kSlots; ++i) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream[i], cudaStreamNonBlocking);
+        auto &k = s->slot[i];
+        alloc(&k.value, n_val * ev), alloc(&k.gvalue, n_val * ev);
+        alloc(&k.loc, n_pts * 2 * el), alloc(&k.gloc, n_pts * 2 * el);
+        alloc(&k.attn, n_pts * el), alloc(&k.gattn, n_pts * el);
+        alloc(&k.gout, n_out * ev), alloc(&k.out, n_out * ev);
+        alloc(&k.ws, s->ws_bytes);
+    }
+    if (e != cudaSuccess) {
+        session_free(s);
+        return check_cuda(e, "msda_host_session_create");
+    }
+    *session = s;
+    return MSDA_OK;
+}
+
+void msda_host_session_destroy(msda_host_session *session) { session_free(session); }
+
+int msda_host_forward_backward(msda_host_session *s, const void *value, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                               const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                               void *grad_attn_weight, const msda_dims *dims, unsigned flags)
+{
+    tl_error[0] = 0;
+    if (!s) return fail(MSDA_ERR_INVALID_ARGUMENT, "session is null");
+    if (int rc = check_dims(dims, s->dtype)) return rc;
+    const msda_dims &mx = s->max_dims;
+    if (dims->spatial_size > mx.spatial_size || dims->num_heads * dims->channels > mx.num_heads * mx.channels ||
+        dims->num_query * dims->num_heads * dims->num_levels * dims->num_point >
+            mx.num_query * mx.num_heads * mx.num_levels * mx.num_point ||
+        dims->num_query * dims->num_heads * dims->channels > mx.num_query * mx.num_heads * mx.channels ||
+        dims->spatial_size * dims->num_heads * dims->channels > mx.spatial_size * mx.num_heads * mx.channels ||
+        dims->num_levels > mx.num_levels)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "problem exceeds the session's max_dims");
+    if (int rc = check_cuda(cudaSetDevice(s->device), "cudaSetDevice")) return rc;
+
+    const size_t ev = dtype_size(s->dtype), el = s->dtype == MSDA_F64 ? 8 : 4;
+    const size_t img_val = (size_t)(dims->spatial_size * dims->num_heads * dims->channels) * ev;
+    const size_t img_pts = (size_t)(dims->num_query * dims->num_heads * dims->num_levels * dims->num_point) * el;
+    const size_t img_out = (size_t)(dims->num_query * dims->num_heads * dims->channels) * ev;
+    constexpr int K = msda_host_session::kSlots;
+
+    // level metadata: one small upload, made visible to every slot stream through an event
+    cudaEvent_t meta_ready;
+    if (int rc = check_cuda(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming), "event")) return rc;
+    cudaMemcpyAsync(s->d_shapes, spatial_shapes, sizeof(int64_t) * 2 * dims->num_levels, cudaMemcpyHostToDevice,
+                    s->stream[0]);
+    cudaMemcpyAsync(s->d_lsi, level_start_index, sizeof(int64_t) * dims->num_levels, cudaMemcpyHostToDevice,
+                    s->stream[0]);
+    cudaEventRecord(meta_ready, s->stream[0]);
+    for (int i = 1; i < K; ++i) cudaStreamWaitEvent(s->stream[i], meta_ready, 0);
+
+    int rc = MSDA_OK;
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < dims->batch && rc == MSDA_OK; b0 += s->chunk, slot = (slot + 1) % K) {
+        const int64_t nb = (dims->batch - b0 < s->chunk) ? dims->batch - b0 : s->chunk;
+        auto &k = s->slot[slot];
+        cudaStream_t st = s->stream[slot];
+        msda_dims cd = *dims;
+        cd.batch = nb;
+        const char *hv = (const char *)value + b0 * img_val;
+        cudaMemcpyAsync(k.value, hv, nb * img_val, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(k.loc, (const char *)sampling_loc + b0 * img_pts * 2, nb * img_pts * 2,
+                        cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(k.attn, (const char *)attn_weight + b0 * img_pts, nb * img_pts, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(k.gout, (const char *)grad_output + b0 * img_out, nb * img_out, cudaMemcpyHostToDevice, st);
+        rc = msda_forward(k.value, s->d_shapes, s->d_lsi, k.loc, k.attn, k.out, &cd, s->dtype, flags, st);
+        if (rc) break;
+        rc = msda_backward(k.value, s->d_shapes, s->d_lsi, k.loc, k.attn, k.gout, k.gvalue, k.gloc, k.gattn, &cd,
+                           s->dtype, flags | MSDA_FLAG_ZERO_GRAD_VALUE, k.ws, s->ws_bytes, st);
+        if (rc) break;
+        cudaMemcpyAsync((char *)output + b0 * img_out, k.out, nb * img_out, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((char *)grad_value + b0 * img_val, k.gvalue, nb * img_val, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((char *)grad_sampling_loc + b0 * img_pts * 2, k.gloc, nb * img_pts * 2,
+                        cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync((char *)grad_attn_weight + b0 * img_pts, k.gattn, nb * img_pts, cudaMemcpyDeviceToHost, st);
+    }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < K; ++i) {
+        cudaError_t ei = cudaStreamSynchronize(s->stream[i]);
+        if (e == cudaSuccess) e = ei;
+    }
+    cudaEventDestroy(meta_ready);
+    if (rc) return rc;
+    return check_cuda(e, "msda_host_forward_backward");
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+/*
+ * msda.h -- C ABI of the B200 (sm_100a) multi-scale deformable attention library.
+ *
+ * This is the drop-in boundary for the native backend of the reference's models/ops package.
+ * Every entry point takes plain pointers and sizes (no torch / ATen types), enqueues work on the
+ * CUDA stream it is given and returns without synchronising.  The caller owns every buffer; the
+ * library allocates no device memory of its own except inside an msda_host_session.
+ *
+ * What each function replaces in the reference (paths relative to /root/reference):
+ *
+ *   msda_forward    -> ms_deform_attn_forward / ms_deform_attn_cuda_forward
+ *                      models/ops/src/ms_deform_attn.h:20-39, models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80,
+ *                      kernel models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299
+ *   msda_backward   -> ms_deform_attn_backward / ms_deform_attn_cuda_backward
+ *                      models/ops/src/ms_deform_attn.h:41-61, models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153,
+ *                      kernels models/ops/src/cuda/ms_deform_im2col_cuda.cuh:301-920, launcher :956-1327
+ *   (pybind surface models/ops/src/vision.cpp:13-16 is rebuilt in Python over these two calls.)
+ *
+ * Tensor layouts (contiguous, row-major; identical to the reference):
+ *   value         (N, S, M, D)            dtype T
+ *   spatial_shapes(L, 2) int64 [H_l, W_l] DEVICE memory   level_start_index (L,) int64 DEVICE memory
+ *   sampling_loc  (N, Lq, M, L, P, 2)     (x, y) normalised to [0,1]; dtype LOC(T)
+ *   attn_weight   (N, Lq, M, L, P)        dtype LOC(T)
+ *   output / grad_output (N, Lq, M, D)    dtype T   (viewed as (N, Lq, M*D) by the caller)
+ * with T in {f32, f64, bf16} and LOC(f32)=f32, LOC(f64)=f64, LOC(bf16)=f32 (bf16 carries too few
+ * mantissa bits for pixel coordinates; arithmetic and accumulation are fp32 for f32/bf16, fp64 for f64).
+ *
+ * Differences from the reference, all deliberate:
+ *   - im2col_step (batch chunking, ms_deform_attn_cuda.cu:50-72) does not exist at this level: one launch
+ *     covers the whole batch, so there is no "batch % im2col_step" restriction.
+ *   - launch failures are returned (non-zero + msda_last_error()), not printf'd (.cuh:948-952, 1321-1325).
+ *   - grad_sampling_loc and grad_attn_weight are fully overwritten (no zero-fill needed);
+ *     grad_value is accumulated into and must be zero on entry unless MSDA_FLAG_ZERO_GRAD_VALUE is set.
+ *   - bf16 is new; the reference dispatches float/double only (ms_deform_attn_cuda.cu:64,134).
+ */
+#ifndef MSDA_H_
+#define MSDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* element type of value / output / grad_output / grad_value */
+enum { MSDA_F32 = 0, MSDA_F64 = 1, MSDA_BF16 = 2 };
+
+/* status codes */
+enum {
+    MSDA_OK = 0,
+    MSDA_ERR_INVALID_ARGUMENT = 1, /* null pointer, non-positive dimension, unknown dtype, overflow */
+    MSDA_ERR_WORKSPACE = 2,        /* workspace missing or too small                               */
+    MSDA_ERR_CUDA = 3,             /* a CUDA runtime call or kernel launch failed                  */
+    MSDA_ERR_UNSUPPORTED = 4       /* shape outside what this build instantiates                   */
+};
+
+/* flags */
+enum {
+    MSDA_FLAG_ZERO_GRAD_VALUE = 1u << 0, /* backward: memset grad_value on the stream before accumulating   */
+    MSDA_FLAG_DETERMINISTIC = 1u << 1,   /* backward: bit-reproducible grad_value (order-independent path)  */
+    MSDA_FLAG_FORCE_GENERIC = 1u << 2    /* testing: skip the specialised kernels, use the generic ones     */
+};
+
+/* Problem geometry.  All counts are element counts, not bytes. */
+typedef struct msda_dims {
+    int64_t batch;        /* N  */
+    int64_t spatial_size; /* S = sum_l H_l*W_l */
+    int64_t num_heads;    /* M  */
+    int64_t channels;     /* D  (per head) */
+    int64_t num_levels;   /* L  */
+    int64_t num_query;    /* Lq */
+    int64_t num_point;    /* P  */
+} msda_dims;
+
+int msda_abi_version(void);
+
+/* Thread-local description of the last failure on the calling thread ("" if none). */
+const char *msda_last_error(void);
+
+/* Name of the kernel variant the last successful forward/backward on this thread selected
+ * (e.g. "fwd_vec<f32,D32,L4,P4>" or "bwd_generic<f64>"); for tests and bench logs. */
+const char *msda_last_kernel(void);
+
+/* Kernel launches enqueued by this thread since the counter was last reset (memsets excluded). */
+int64_t msda_launch_count(int reset);
+
+/* out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]) */
+int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                 const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims,
+                 int dtype, unsigned flags, void *cuda_stream);
+
+/* Bytes of device scratch msda_backward needs for this problem (0 for f32/f64 without flags). */
+size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags);
+
+/* grad_value += scatter(w*attn*grad_out); grad_sampling_loc, grad_attn_weight = analytic gradients. */
+int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                  const void *sampling_loc, const void *attn_weight, const void *grad_output,
+                  void *grad_value, void *grad_sampling_loc, void *grad_attn_weight, const msda_dims *dims,
+                  int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/*
+ * Host-buffer path (what a caller without device tensors uses; bench.py's "e2e" leg).
+ * A session owns device buffers and streams sized for `max_dims`; msda_host_forward_backward copies
+ * the inputs host->device image-chunk by image-chunk, runs forward+backward, and copies the four
+ * results back, overlapping copies with kernels.  Host buffers should be page-locked for full
+ * PCIe bandwidth.  spatial_shapes / level_start_index are HOST pointers here.
+ * The call returns after all results have landed in the host buffers.
+ */
+typedef struct msda_host_session msda_host_session;
+
+int msda_host_session_create(msda_host_session **session, const msda_dims *max_dims, int dtype, int device,
+                             int images_per_chunk);
+void msda_host_session_destroy(msda_host_session *session);
+int msda_host_forward_backward(msda_host_session *session, const void *value, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, const void *sampling_loc,
+                               const void *attn_weight, const void *grad_output, void *output,
+                               void *grad_value, void *grad_sampling_loc, void *grad_attn_weight,
+                               const msda_dims *dims, unsigned flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_H_ */

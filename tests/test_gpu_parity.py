@@ -1,0 +1,329 @@
+"""GPU: the sm_100a kernels, called through the C ABI, against the CPU oracle and the reference-made golden vectors.
+
+Parity bar, error = max|got-ref| / max|ref| against the fp64 oracle on the same (rounded) inputs:
+  fp64 <= 1e-12 | fp32 forward <= 1e-5, gradients <= 1e-4 | bf16 I/O (fp32 accumulate, fp32 locations) <= 2e-2
+"""
+import numpy as np
+import pytest
+import torch
+
+from . import helpers
+from .conftest import l2_rel_err, load_golden, max_norm_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {  # dtype -> (forward, gradients)
+    torch.float64: (1e-12, 1e-12),
+    torch.float32: (1e-5, 1e-4),
+    torch.bfloat16: (2e-2, 2e-2),
+}
+
+
+@pytest.fixture(scope="module")
+def lib():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from grit_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def run_kernels(lib, case, dtype, flags=0):
+    t = helpers.to_cuda(case, dtype)
+    out = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"], flags)
+    fwd_kernel = lib.last_kernel()
+    gv, gl, ga = lib.backward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"],
+                              t["grad_out"].view_as(out), flags)
+    bwd_kernel = lib.last_kernel()
+    torch.cuda.synchronize()
+    return dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga, fwd_kernel=fwd_kernel, bwd_kernel=bwd_kernel)
+
+
+def oracle_results(oracle, case):
+    out = oracle.forward(case["value"], case["shapes"], case["level_start"], case["loc"], case["attn"])
+    gv, gl, ga = oracle.backward(case["value"], case["shapes"], case["level_start"], case["loc"], case["attn"],
+                                 case["grad_out"])
+    return dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga)
+
+
+def assert_parity(got, ref, case, dtype, what=""):
+    ftol, gtol = TOL[dtype]
+    f = lambda k: got[k].double().cpu().numpy()
+    assert max_norm_err(f("out"), ref["out"]) <= ftol, f"{what} out"
+    assert l2_rel_err(f("out"), ref["out"]) <= ftol, f"{what} out (l2)"
+    assert max_norm_err(f("grad_value"), ref["grad_value"]) <= gtol, f"{what} grad_value"
+    assert max_norm_err(f("grad_attn"), ref["grad_attn"]) <= gtol, f"{what} grad_attn"
+    keep = ~helpers.tie_mask(case["loc"], case["shapes"]) if dtype != torch.float64 else np.ones(
+        case["loc"].shape[:-1], dtype=bool)
+    gl, rl = f("grad_loc"), ref["grad_loc"]
+    denom = max(np.abs(rl).max(), 1e-300)
+    assert np.abs((gl - rl)[keep]).max() / denom <= gtol, f"{what} grad_sampling_loc"
+
+
+# ---- golden vectors made by the reference itself ---------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["testpy_grad_D30", "testpy_grad_D32", "testpy_grad_D64", "testpy_grad_D71",
+                                  "oob_small", "det_small"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+def test_golden_vectors(lib, name, dtype):
+    g = load_golden(name)
+    case = helpers.rounded_case(g, dtype)
+    got = run_kernels(lib, case, dtype)
+    if dtype == torch.float64:
+        ref = {k: g[k] for k in ("out", "grad_value", "grad_loc", "grad_attn")}  # straight from the reference
+    else:
+        from oracle import msda_oracle
+        ref = oracle_results(msda_oracle, case)
+    assert_parity(got, ref, case, dtype, name)
+
+
+def test_reference_test_recipe_forward(lib):
+    """models/ops/test.py:31-60 -- same inputs (seed 3 stream), same acceptance rules."""
+    g = load_golden("testpy_fwd_double")
+    t = helpers.to_cuda(g, torch.float64)
+    out = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"])
+    assert torch.allclose(out.cpu(), torch.from_numpy(g["out"]))
+    g = load_golden("testpy_fwd_float")
+    t = helpers.to_cuda(g, torch.float32)
+    out = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"])
+    assert torch.allclose(out.cpu(), torch.from_numpy(g["out"]), rtol=1e-2, atol=1e-3)
+    assert max_norm_err(out.cpu().numpy(), g["out"]) < 1e-5
+
+
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_reference_gradcheck(lib, channels):
+    """models/ops/test.py:63-78, 85-86 -- numerical gradcheck in fp64 for D in {30, 32, 64, 71}."""
+    from grit_b200 import MSDeformAttnFunction
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long).cuda()
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    value = (torch.rand(N, S, M, channels) * 0.01).cuda().double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2).cuda().double().requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P).cuda() + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, attn, 2))
+
+
+# ---- seeded random problems against the C oracle -----------------------------------------------------------------------
+
+SMALL_PYR = [(12, 20), (6, 10), (3, 5), (2, 3)]
+RANDOM_CASES = [
+    # N, Lq,  M, D,   shapes,                         P, expected forward kernel for fp32
+    (2, 37, 8, 32, SMALL_PYR, 4, "fwd_vec<f32,D32,L4,P4>"),
+    (2, 19, 8, 64, SMALL_PYR, 4, "fwd_vec<f32,D64,L4,P4>"),
+    (1, 23, 4, 16, SMALL_PYR, 4, "fwd_vec<f32,D16,L4,P4>"),
+    (1, 11, 2, 128, SMALL_PYR, 4, "fwd_vec<f32,D128,L4,P4>"),
+    (2, 13, 8, 32, SMALL_PYR, 8, "fwd_vec<f32,D32,L4,P8>"),
+    (2, 29, 8, 32, [(9, 14)], 4, "fwd_vec<f32,D32,L1,P4>"),
+    (2, 17, 3, 5, [(5, 7), (1, 1), (2, 3)], 2, "fwd_generic<f32>"),
+    (1, 9, 2, 71, [(4, 4), (2, 2)], 3, "fwd_generic<f32>"),
+    (3, 5, 8, 32, [(7, 9), (4, 5), (2, 3)], 4, "fwd_generic<f32>"),
+    (1, 6, 1, 40, [(3, 1), (1, 5)], 1, "fwd_generic<f32>"),
+]
+
+
+@pytest.mark.parametrize("spec", RANDOM_CASES, ids=lambda s: f"N{s[0]}Lq{s[1]}M{s[2]}D{s[3]}L{len(s[4])}P{s[5]}")
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
+def test_random_problems_vs_oracle(lib, oracle, spec, dtype):
+    N, Lq, M, D, shapes, P, kernel = spec
+    case = helpers.rounded_case(helpers.make_inputs(N, Lq, M, D, shapes, P, seed=hash((N, Lq, D, P)) % 1000,
+                                                    lo=-0.2, hi=1.2), dtype)
+    got = run_kernels(lib, case, dtype)
+    if dtype == torch.float32:
+        assert got["fwd_kernel"] == kernel
+        assert got["bwd_kernel"] == kernel.replace("fwd", "bwd")
+    if dtype == torch.float64:
+        assert got["fwd_kernel"] == "fwd_generic<f64>"
+    assert_parity(got, oracle_results(oracle, case), case, dtype, str(spec[:4]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_specialised_and_generic_kernels_agree(lib, oracle, dtype):
+    case = helpers.rounded_case(helpers.make_inputs(2, 50, 8, 32, SMALL_PYR, 4, seed=5), dtype)
+    fast = run_kernels(lib, case, dtype)
+    slow = run_kernels(lib, case, dtype, flags=lib.FLAG_FORCE_GENERIC)
+    assert fast["fwd_kernel"].startswith("fwd_vec") and slow["fwd_kernel"].startswith("fwd_generic")
+    ref = oracle_results(oracle, case)
+    assert_parity(fast, ref, case, dtype, "vec")
+    assert_parity(slow, ref, case, dtype, "generic")
+
+
+def test_edge_cases(lib, oracle):
+    """Empty query set, NaN / far out-of-range locations, single-pixel level, points exactly on the window edge."""
+    shapes = [(1, 1), (2, 3)]
+    case = helpers.make_inputs(1, 6, 2, 4, shapes, 2, seed=1)
+    case["loc"][0, 0] = np.nan
+    case["loc"][0, 1] = 7.0
+    case["loc"][0, 2] = -7.0
+    case["loc"][0, 3, :, 1, :, 0] = 1.0 + 0.5 / 3  # w_im == W: just outside the (-1, W) window
+    case["loc"][0, 4, :, 1, :, 1] = -0.5 / 2       # h_im == -1: just outside
+    for dtype in (torch.float64, torch.float32):
+        c = helpers.rounded_case(case, dtype)
+        got = run_kernels(lib, c, dtype)
+        ref = oracle_results(oracle, c)
+        out = got["out"].double().cpu().numpy()
+        assert np.all(out[0, :3] == 0) and np.all(np.isfinite(out))
+        assert np.all(got["grad_loc"].cpu().numpy()[0, :3] == 0) and np.all(got["grad_attn"].cpu().numpy()[0, :3] == 0)
+        assert max_norm_err(out, ref["out"]) < TOL[dtype][0]
+        assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref["grad_value"]) < TOL[dtype][1]
+    # Lq = 0
+    t = helpers.to_cuda(case, torch.float32)
+    out = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"][:, :0].contiguous(),
+                      t["attn"][:, :0].contiguous())
+    assert tuple(out.shape) == (1, 0, 8)
+    gv, gl, ga = lib.backward(t["value"], t["shapes"], t["level_start"], t["loc"][:, :0].contiguous(),
+                              t["attn"][:, :0].contiguous(), out)
+    assert float(gv.abs().sum()) == 0 and gl.numel() == 0 and ga.numel() == 0
+
+
+def test_argument_checks_on_gpu(lib):
+    t = helpers.to_cuda(helpers.make_inputs(1, 3, 2, 4, [(2, 2)], 1), torch.float32)
+    with pytest.raises(RuntimeError, match="has to be contiguous"):
+        lib.forward(t["value"].transpose(1, 2), t["shapes"], t["level_start"], t["loc"], t["attn"])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        lib.forward(t["value"], t["shapes"].cpu(), t["level_start"], t["loc"], t["attn"])
+    with pytest.raises(RuntimeError, match="dtype"):
+        lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"].double(), t["attn"])
+    with pytest.raises(RuntimeError, match="not implemented for"):
+        lib.forward(t["value"].half(), t["shapes"], t["level_start"], t["loc"], t["attn"])
+
+
+def test_batch_not_multiple_of_im2col_step_is_accepted(lib, oracle):
+    """The reference fails for batch % min(batch, im2col_step) != 0 (ms_deform_attn_cuda.cu:52); one launch here."""
+    from grit_b200 import MSDeformAttnFunction
+    case = helpers.make_inputs(5, 7, 2, 8, [(4, 4), (2, 2)], 2, seed=9)
+    t = helpers.to_cuda(case, torch.float64)
+    out = MSDeformAttnFunction.apply(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"], 2)
+    assert max_norm_err(out.cpu().numpy(), oracle_results(oracle, case)["out"]) < 1e-12
+
+
+# ---- full-size problems: size-independent properties (the oracle would take minutes here) ---------------------------
+
+@pytest.mark.parametrize("dtype,D,Lq", [(torch.float32, 32, 22223), (torch.float32, 64, 150), (torch.bfloat16, 64, 150)])
+def test_full_size_adjoint_and_linearity(lib, dtype, D, Lq):
+    """out is linear in value and in attn, so with g = grad_out:
+         <out, g> == <value, grad_value> == <attn, grad_attn>            (adjoint identities)
+         fwd(2*value) == 2*fwd(value)                                     (linearity)
+       checked at the 800x1333 pyramid (S = 22223), 8 heads, 4x4 points."""
+    torch.manual_seed(0)
+    N, M, L, P = 2, 8, 4, 4
+    shapes_l = helpers.PYRAMID_800x1333
+    S = sum(h * w for h, w in shapes_l)
+    dev = "cuda"
+    shapes = torch.tensor(shapes_l, device=dev)
+    lsi = torch.from_numpy(helpers.level_start(shapes_l)).to(dev)
+    value = torch.randn(N, S, M, D, device=dev).to(dtype)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=dev) * 1.1 - 0.05
+    attn = torch.softmax(torch.randn(N, Lq, M, L * P, device=dev), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, device=dev).to(dtype)
+    out = lib.forward(value, shapes, lsi, loc, attn)
+    gv, gl, ga = lib.backward(value, shapes, lsi, loc, attn, gout)
+    lhs = (out.double() * gout.double()).sum().item()
+    via_value = (value.double() * gv.double()).sum().item()
+    via_attn = (attn.double() * ga.double()).sum().item()
+    scale = (out.double().abs() * gout.double().abs()).sum().item()
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert abs(lhs - via_value) / scale < tol
+    assert abs(lhs - via_attn) / scale < tol
+    out2 = lib.forward((value.float() * 2).to(dtype), shapes, lsi, loc, attn)
+    assert torch.equal(out2, (out.float() * 2).to(dtype))  # scaling by 2 is exact in binary floating point
+    assert torch.isfinite(gl).all()
+
+
+def test_full_size_sample_rows_vs_oracle(lib, oracle):
+    """800x1333 pyramid, fp32, D=32: a strided subset of query rows is checked against the fp64 oracle."""
+    N, M, D, P = 1, 8, 32, 4
+    shapes_l = helpers.PYRAMID_800x1333
+    case = helpers.make_inputs(N, 4096, M, D, shapes_l, P, seed=3, dtype=np.float32)
+    case = helpers.rounded_case(case, torch.float32)
+    got = run_kernels(lib, case, torch.float32)
+    assert got["fwd_kernel"] == "fwd_vec<f32,D32,L4,P4>"
+    assert_parity(got, oracle_results(oracle, case), case, torch.float32, "800x1333")
+
+
+# ---- the module and the autograd Function ----------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["module_ref2", "module_ref4"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_module_matches_reference_module(lib, name, dtype):
+    """MSDeformAttn.forward/backward vs the reference module's stored outputs and gradients (fp64 golden)."""
+    from grit_b200 import MSDeformAttn
+    g = load_golden(name)
+    mod = MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"]))
+    mod.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    mod = mod.to("cuda", dtype)
+    cu = lambda k: torch.from_numpy(g[k]).to("cuda")
+    query = cu("query").to(dtype).requires_grad_(True)
+    src = cu("input_flatten").to(dtype).requires_grad_(True)
+    out = mod(query, cu("reference_points").to(dtype), src, cu("shapes"), cu("level_start"), cu("padding_mask"))
+    out.backward(cu("grad_out").to(dtype))
+    tol = 1e-10 if dtype == torch.float64 else 2e-4
+    assert max_norm_err(out.detach().cpu().numpy(), g["out"]) < tol
+    assert max_norm_err(query.grad.cpu().numpy(), g["grad_query"]) < tol
+    assert max_norm_err(src.grad.cpu().numpy(), g["grad_input_flatten"]) < tol
+    for k, p in mod.named_parameters():
+        assert max_norm_err(p.grad.cpu().numpy(), g["grad." + k]) < tol, k
+
+
+def test_module_invalid_reference_points(lib):
+    from grit_b200 import MSDeformAttn
+    mod = MSDeformAttn(32, 2, 4, 2).cuda()
+    shapes = torch.tensor([[4, 4], [2, 2]], device="cuda")
+    lsi = torch.tensor([0, 16], device="cuda")
+    with pytest.raises(ValueError, match="Last dim of reference_points must be 2 or 4"):
+        mod(torch.zeros(1, 3, 32, device="cuda"), torch.zeros(1, 3, 2, 3, device="cuda"),
+            torch.zeros(1, 20, 32, device="cuda"), shapes, lsi)
+    with pytest.raises(AssertionError):
+        mod(torch.zeros(1, 3, 32, device="cuda"), torch.zeros(1, 3, 2, 2, device="cuda"),
+            torch.zeros(1, 21, 32, device="cuda"), shapes, lsi)
+
+
+def test_function_backward_tuple_and_bf16_autograd(lib, oracle):
+    from grit_b200 import MSDeformAttnFunction
+    case = helpers.rounded_case(helpers.make_inputs(2, 10, 8, 32, SMALL_PYR, 4, seed=2), torch.bfloat16)
+    t = helpers.to_cuda(case, torch.bfloat16)
+    value = t["value"].requires_grad_(True)
+    loc = t["loc"].requires_grad_(True)
+    attn = t["attn"].requires_grad_(True)
+    out = MSDeformAttnFunction.apply(value, t["shapes"], t["level_start"], loc, attn, 64)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (2, 10, 256)
+    out.backward(t["grad_out"])
+    assert value.grad.dtype == torch.bfloat16 and loc.grad.dtype == torch.float32
+    ref = oracle_results(oracle, case)
+    assert max_norm_err(value.grad.double().cpu().numpy(), ref["grad_value"]) < 2e-2
+    assert t["shapes"].grad is None
+
+
+def test_reference_pybind_surface(lib, oracle):
+    """The MultiScaleDeformableAttention compat module: same call shapes as models/ops/src/vision.cpp:14-15."""
+    import grit_b200
+    msda_mod = grit_b200.install_as_reference_ops()
+    case = helpers.make_inputs(2, 5, 2, 6, [(3, 4), (2, 2)], 2, seed=4)
+    t = helpers.to_cuda(case, torch.float64)
+    out = msda_mod.ms_deform_attn_forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"], 64)
+    grads = msda_mod.ms_deform_attn_backward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"],
+                                             t["grad_out"], 64)
+    ref = oracle_results(oracle, case)
+    assert isinstance(grads, list) and len(grads) == 3
+    assert max_norm_err(out.cpu().numpy(), ref["out"]) < 1e-12
+    for got, key in zip(grads, ("grad_value", "grad_loc", "grad_attn")):
+        assert max_norm_err(got.cpu().numpy(), ref[key]) < 1e-12
+
+
+def test_host_session_matches_device_path(lib, oracle):
+    """msda_host_forward_backward (host buffers, chunked + pipelined) == oracle, incl. a ragged last chunk."""
+    case = helpers.rounded_case(helpers.make_inputs(5, 33, 8, 32, SMALL_PYR, 4, seed=8), torch.float32)
+    f32 = lambda k: torch.from_numpy(case[k]).float().contiguous().pin_memory()
+    value, loc, attn, gout = f32("value"), f32("loc"), f32("attn"), f32("grad_out")
+    shapes, lsi = torch.from_numpy(case["shapes"]), torch.from_numpy(case["level_start"])
+    out = torch.empty(5, 33, 256).pin_memory()
+    gv, gl, ga = torch.empty_like(value).pin_memory(), torch.empty_like(loc).pin_memory(), torch.empty_like(attn).pin_memory()
+    dims = lib.MsdaDims(5, value.shape[1], 8, 32, 4, 33, 4)
+    sess = lib.HostSession(dims, torch.float32, device=0, images_per_chunk=2)
+    sess.forward_backward(value, shapes, lsi, loc, attn, gout, out, gv, gl, ga)
+    sess.close()
+    ref = oracle_results(oracle, case)
+    assert max_norm_err(out.numpy(), ref["out"]) < 1e-5
+    assert max_norm_err(gv.numpy(), ref["grad_value"]) < 1e-4
+    assert max_norm_err(ga.numpy(), ref["grad_attn"]) < 1e-4
