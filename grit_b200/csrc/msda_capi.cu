@@ -82,6 +82,8 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
 {
     if (flags & MSDA_FLAG_FORCE_GENERIC) return false;
     if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
+    if (d->batch * d->num_query * d->num_heads >= ((int64_t)1 << 31)) return false;  // 32-bit row index
+    if (d->num_heads * d->num_query >= ((int64_t)1 << 31)) return false;
     return d->spatial_size * d->num_heads * d->channels < ((int64_t)1 << 31);
 }
 

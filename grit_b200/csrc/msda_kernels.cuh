@@ -91,6 +91,7 @@ __device__ __forceinline__ void red_add_chunk(float *p, const float (&g)[E], flo
 struct Taps {
     int pix;          // start + r0*W + c0  (pixel index of the top-left tap inside the image)
     int W;            // row pitch in pixels
+    bool live;        // inside the (-1, size) window; dead points contribute nothing and get zero gradients
     bool tl, tr, bl, br;
     float lh, lw, hh, hw;
 };
@@ -98,14 +99,15 @@ struct Taps {
 __device__ __forceinline__ Taps resolve_taps(float x, float y, int H, int W, int start)
 {
     Taps t;
-    const float h_im = fmaf(y, (float)H, -0.5f);
-    const float w_im = fmaf(x, (float)W, -0.5f);
-    const bool live = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;  // false for NaN
+    float h_im = fmaf(y, (float)H, -0.5f);
+    float w_im = fmaf(x, (float)W, -0.5f);
+    t.live = h_im > -1.f && w_im > -1.f && h_im < (float)H && w_im < (float)W;  // false for NaN
+    if (!t.live) h_im = w_im = 0.f;  // keeps every derived quantity finite; all four taps end up invalid
     const float hf = floorf(h_im), wf = floorf(w_im);
-    const int r0 = live ? (int)hf : 0, c0 = live ? (int)wf : 0;
+    const int r0 = (int)hf, c0 = (int)wf;
     t.lh = h_im - hf, t.lw = w_im - wf;
     t.hh = 1.f - t.lh, t.hw = 1.f - t.lw;
-    const bool top = live && r0 >= 0, bot = live && r0 + 1 < H;
+    const bool top = t.live && r0 >= 0, bot = t.live && r0 + 1 < H;
     const bool lef = c0 >= 0, rig = c0 + 1 < W;
     t.tl = top && lef, t.tr = top && rig, t.bl = bot && lef, t.br = bot && rig;
     t.pix = start + r0 * W + c0;
@@ -146,10 +148,11 @@ msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
 
     const int lane = threadIdx.x & 31;
     const int g = lane / LPT, sub = lane % LPT;
-    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);  // (b*Lq + q)*M + m
-    if (row >= rows) return;
-    const int m = (int)(row % M);
-    const int64_t b = row / ((int64_t)M * Lq);
+    const unsigned urow = blockIdx.x * WARPS + (threadIdx.x >> 5);  // (b*Lq + q)*M + m, < 2^31 (host-checked)
+    if (urow >= (unsigned)rows) return;
+    const int64_t row = urow;
+    const int m = (int)(urow % (unsigned)M);
+    const int64_t b = urow / ((unsigned)M * (unsigned)Lq);
     const int MD = M * D;
     const T *vbase = value + (b * S * M + m) * (int64_t)D + sub * E;
     const float2 *lrow = reinterpret_cast<const float2 *>(loc) + row * LP;
@@ -164,8 +167,8 @@ msda_fwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
         const int pt = it * G + g;
         const int l = pt / P;
         const float2 xy = __ldg(lrow + pt);
-        const float a = __ldg(arow + pt);
         const Taps t = resolve_taps(xy.x, xy.y, sH[l], sW[l], sStart[l]);
+        const float a = t.live ? __ldg(arow + pt) : 0.f;  // the reference never reads attn of a skipped point
         const T *p0 = vbase + (int64_t)t.pix * MD;
         const T *p1 = p0 + (int64_t)t.W * MD;
         float v0[E], v1[E], v2[E], v3[E];
@@ -212,10 +215,11 @@ msda_bwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
 
     const int lane = threadIdx.x & 31;
     const int g = lane / LPT, sub = lane % LPT;
-    const int64_t row = (int64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int m = (int)(row % M);
-    const int64_t b = row / ((int64_t)M * Lq);
+    const unsigned urow = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (urow >= (unsigned)rows) return;
+    const int64_t row = urow;
+    const int m = (int)(urow % (unsigned)M);
+    const int64_t b = urow / ((unsigned)M * (unsigned)Lq);
     const int MD = M * D;
     const int64_t img = (b * S * M + m) * (int64_t)D + sub * E;
     const T *vbase = value + img;
@@ -233,9 +237,9 @@ msda_bwd_vec(const T *__restrict__ value, const int64_t *__restrict__ shapes, co
         const int pt = it * G + g;
         const int l = pt / P;
         const float2 xy = __ldg(lrow + pt);
-        const float a = __ldg(arow + pt);
         const int H = sH[l], W = sW[l];
         const Taps t = resolve_taps(xy.x, xy.y, H, W, sStart[l]);
+        const float a = t.live ? __ldg(arow + pt) : 0.f;
         const int64_t o0 = (int64_t)t.pix * MD, o1 = o0 + (int64_t)W * MD;
         float v0[E], v1[E], v2[E], v3[E];
 #pragma unroll
@@ -310,6 +314,7 @@ template <typename C>
 struct TapsG {
     int64_t pix;
     int W;
+    bool live;
     bool tl, tr, bl, br;
     C lh, lw, hh, hw;
 };
@@ -318,14 +323,15 @@ template <typename C>
 __device__ __forceinline__ TapsG<C> resolve_taps_g(C x, C y, int H, int W, int start)
 {
     TapsG<C> t;
-    const C h_im = y * (C)H - (C)0.5;
-    const C w_im = x * (C)W - (C)0.5;
-    const bool live = h_im > (C)-1 && w_im > (C)-1 && h_im < (C)H && w_im < (C)W;
+    C h_im = y * (C)H - (C)0.5;
+    C w_im = x * (C)W - (C)0.5;
+    t.live = h_im > (C)-1 && w_im > (C)-1 && h_im < (C)H && w_im < (C)W;
+    if (!t.live) h_im = w_im = (C)0;
     const C hf = floor(h_im), wf = floor(w_im);
-    const int r0 = live ? (int)hf : 0, c0 = live ? (int)wf : 0;
+    const int r0 = (int)hf, c0 = (int)wf;
     t.lh = h_im - hf, t.lw = w_im - wf;
     t.hh = (C)1 - t.lh, t.hw = (C)1 - t.lw;
-    const bool top = live && r0 >= 0, bot = live && r0 + 1 < H;
+    const bool top = t.live && r0 >= 0, bot = t.live && r0 + 1 < H;
     const bool lef = c0 >= 0, rig = c0 + 1 < W;
     t.tl = top && lef, t.tr = top && rig, t.bl = bot && lef, t.br = bot && rig;
     t.pix = (int64_t)start + (int64_t)r0 * W + c0;
@@ -363,7 +369,7 @@ msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
             for (int p = 0; p < P; ++p) {
                 const int k = l * P + p;
                 const TapsG<C> t = resolve_taps_g<C>(lrow[2 * k], lrow[2 * k + 1], H, W, start);
-                const C a = arow[k];
+                const C a = t.live ? arow[k] : (C)0;
                 const T *p0 = vimg + t.pix * MD + c;
                 const T *p1 = p0 + (int64_t)W * MD;
                 const C v0 = t.tl ? to_c<C, T>(p0[0]) : (C)0;
@@ -408,7 +414,7 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
         for (int p = 0; p < P; ++p) {
             const int k = l * P + p;
             const TapsG<C> t = resolve_taps_g<C>(lrow[2 * k], lrow[2 * k + 1], H, W, start);
-            const C a = arow[k];
+            const C a = t.live ? arow[k] : (C)0;
             const C w0 = t.hh * t.hw, w1 = t.hh * t.lw, w2 = t.lh * t.hw, w3 = t.lh * t.lw;
             const int64_t o0 = img + t.pix * MD, o1 = o0 + (int64_t)W * MD;
             C s_a = 0, s_x = 0, s_y = 0;
