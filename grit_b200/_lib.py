@@ -56,6 +56,8 @@ def load():
         lib.msda_last_kernel.restype = ctypes.c_char_p
         lib.msda_launch_count.restype = ctypes.c_int64
         lib.msda_launch_count.argtypes = [ctypes.c_int]
+        lib.msda_set_tuning.restype = ctypes.c_int
+        lib.msda_set_tuning.argtypes = [ctypes.c_char_p, ctypes.c_int]
         lib.msda_forward.restype = ctypes.c_int
         lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint, vp]
         lib.msda_backward_workspace_bytes.restype = ctypes.c_size_t
@@ -83,6 +85,14 @@ def last_kernel() -> str:
 
 def launch_count(reset: bool = False) -> int:
     return int(load().msda_launch_count(1 if reset else 0))
+
+
+def set_tuning(key: str, value: int) -> int:
+    """A/B knob of the library (include/msda.h: msda_set_tuning); returns the previous value."""
+    prev = load().msda_set_tuning(key.encode(), int(value))
+    if prev < 0:
+        raise KeyError(key)
+    return prev
 
 
 def _raise(lib, rc, what):

@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstring>
 
-#include "msda_kernels.cuh"
+#include "msda_kernels_v2.cuh"
+
+#include <atomic>
 
 namespace {
 
@@ -63,6 +65,11 @@ int check_dims(const msda_dims *d, int dtype)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 constexpr int kWarps = 8;
+
+// Process-wide tuning knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/).
+std::atomic<int> g_variant{2};     // 1: first-generation kernels, 2: resolve-once kernels
+std::atomic<int> g_head_major{0};  // v2 only: 0 = rows in memory order (b,q,m), 1 = (b,m,q)
+std::atomic<int> g_warps{8};       // v2 warps per CTA for the flagship specialisation: 4, 8 or 16
 
 struct Geometry {
     int64_t rows;
@@ -150,6 +157,103 @@ bool launch_bwd_vec(const msda_dims *d, const Geometry &g, const void *value, co
     return false;
 }
 
+template <typename T, int DD, int LL, int PP, int W, bool HM>
+void fwd_v2_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
+                   const void *loc, const void *attn, void *out, cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((rows + W - 1) / W);
+    msda::msda_fwd_v2<T, DD, LL, PP, W, HM><<<grid, W * 32, 0, st>>>(
+        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
+        (int)d->num_heads, (int)d->num_query, rows);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v2<%s,D%d,L%d,P%d,w%d,%s>", tname<T>(), DD, LL, PP, W,
+             HM ? "head-major" : "row-major");
+}
+
+template <typename T, int DD, int LL, int PP, int W, bool HM>
+void bwd_v2_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
+                   const void *loc, const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn,
+                   cudaStream_t st)
+{
+    const unsigned grid = (unsigned)((rows + W - 1) / W);
+    msda::msda_bwd_v2<T, DD, LL, PP, W, HM><<<grid, W * 32, 0, st>>>(
+        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, gv_acc,
+        (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rows);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v2<%s,D%d,L%d,P%d,w%d,%s>", tname<T>(), DD, LL, PP, W,
+             HM ? "head-major" : "row-major");
+}
+
+template <int DD, int LL, int PP, int E>
+constexpr bool v2_ok()
+{
+    constexpr int LPT = DD / E, G = 32 / LPT, LP = LL * PP, PPG = LP / G;
+    return DD % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0 && PPG >= 1 && PPG <= LPT &&
+           (PPG & (PPG - 1)) == 0;
+}
+
+template <typename T>
+bool launch_fwd_v2(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                   const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+    const bool hm = g_head_major.load() != 0;
+    const int w = g_warps.load();
+#define X(DD, LL, PP)                                                                                        \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                  \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                         \
+            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                            \
+                if (w == 4) {                                                                                \
+                    hm ? fwd_v2_launch<T, DD, LL, PP, 4, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)   \
+                       : fwd_v2_launch<T, DD, LL, PP, 4, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st); \
+                    return true;                                                                             \
+                }                                                                                            \
+                if (w == 16) {                                                                               \
+                    hm ? fwd_v2_launch<T, DD, LL, PP, 16, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)  \
+                       : fwd_v2_launch<T, DD, LL, PP, 16, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st);\
+                    return true;                                                                             \
+                }                                                                                            \
+            }                                                                                                \
+            hm ? fwd_v2_launch<T, DD, LL, PP, 8, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)    \
+               : fwd_v2_launch<T, DD, LL, PP, 8, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st);  \
+            return true;                                                                                     \
+        }                                                                                                    \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+    return false;
+}
+
+template <typename T>
+bool launch_bwd_v2(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
+                   const int64_t *lsi, const void *loc, const void *attn, const void *gout, float *gv_acc,
+                   void *gloc, void *gattn, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+    const bool hm = g_head_major.load() != 0;
+    const int w = g_warps.load();
+#define ARGS d, g.rows, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st
+#define X(DD, LL, PP)                                                                                        \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                  \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                         \
+            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                            \
+                if (w == 4) {                                                                                \
+                    hm ? bwd_v2_launch<T, DD, LL, PP, 4, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 4, false>(ARGS);  \
+                    return true;                                                                             \
+                }                                                                                            \
+                if (w == 16) {                                                                               \
+                    hm ? bwd_v2_launch<T, DD, LL, PP, 16, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 16, false>(ARGS);\
+                    return true;                                                                             \
+                }                                                                                            \
+            }                                                                                                \
+            hm ? bwd_v2_launch<T, DD, LL, PP, 8, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 8, false>(ARGS);  \
+            return true;                                                                                     \
+        }                                                                                                    \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+#undef ARGS
+    return false;
+}
+
 template <typename T, typename C>
 void launch_fwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
                         const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st,
@@ -185,6 +289,16 @@ const char *msda_last_error(void) { return tl_error; }
 
 const char *msda_last_kernel(void) { return tl_kernel; }
 
+int msda_set_tuning(const char *key, int value)
+{
+    std::atomic<int> *knob = nullptr;
+    if (key && !strcmp(key, "variant")) knob = &g_variant;
+    if (key && !strcmp(key, "head_major")) knob = &g_head_major;
+    if (key && !strcmp(key, "warps")) knob = &g_warps;
+    if (!knob) return -1;
+    return knob->exchange(value);
+}
+
 int64_t msda_launch_count(int reset)
 {
     const int64_t n = tl_launches;
@@ -209,12 +323,18 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        if (dtype == MSDA_F32)
-            done = launch_fwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                         output, st);
-        else
-            done = launch_fwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                                 attn_weight, output, st);
+        if (g_variant.load() == 2) {
+            done = dtype == MSDA_F32 ? launch_fwd_v2<float>(dims, g, value, spatial_shapes, level_start_index,
+                                                           sampling_loc, attn_weight, output, st)
+                                     : launch_fwd_v2<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index,
+                                                                   sampling_loc, attn_weight, output, st);
+        }
+        if (!done)
+            done = dtype == MSDA_F32 ? launch_fwd_vec<float>(dims, g, value, spatial_shapes, level_start_index,
+                                                            sampling_loc, attn_weight, output, st)
+                                     : launch_fwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes,
+                                                                    level_start_index, sampling_loc, attn_weight,
+                                                                    output, st);
     }
     if (!done) {
         if (dtype == MSDA_F32)
@@ -283,13 +403,23 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) && aligned16(gv_acc) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
         (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0) {
-        if (dtype == MSDA_F32)
-            done = launch_bwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                         grad_output, (float *)gv_acc, grad_sampling_loc, grad_attn_weight, st);
-        else
-            done = launch_bwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                                 attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
-                                                 grad_attn_weight, st);
+        if (g_variant.load() == 2) {
+            done = dtype == MSDA_F32
+                       ? launch_bwd_v2<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                              attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                              grad_attn_weight, st)
+                       : launch_bwd_v2<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                                      attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                      grad_attn_weight, st);
+        }
+        if (!done)
+            done = dtype == MSDA_F32
+                       ? launch_bwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
+                                               attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                               grad_attn_weight, st)
+                       : launch_bwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index,
+                                                       sampling_loc, attn_weight, grad_output, (float *)gv_acc,
+                                                       grad_sampling_loc, grad_attn_weight, st);
     }
     if (!done) {
         if (dtype == MSDA_F32)

@@ -87,6 +87,10 @@ const char *msda_last_kernel(void);
 /* Kernel launches enqueued by this thread since the counter was last reset (memsets excluded). */
 int64_t msda_launch_count(int reset);
 
+/* Tuning / A-B testing knob (process-wide).  Keys: "variant" (1 | 2), "head_major" (0 | 1), "warps" (4 | 8 | 16).
+ * Returns the previous value, or -1 for an unknown key.  Results do not depend on the knobs beyond fp rounding. */
+int msda_set_tuning(const char *key, int value);
+
 /* out[b,q,m,:] = sum_{l,p} attn[b,q,m,l,p] * bilinear(value_l[b,:,m,:], loc[b,q,m,l,p]) */
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims,

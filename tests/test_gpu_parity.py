@@ -250,9 +250,9 @@ def test_module_matches_reference_module(lib, name, dtype):
     """MSDeformAttn.forward/backward vs the reference module's stored outputs and gradients (fp64 golden)."""
     from grit_b200 import MSDeformAttn
     g = load_golden(name)
-    mod = MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"]))
+    mod = MSDeformAttn(int(g["d_model"]), int(g["n_levels"]), int(g["n_heads"]), int(g["n_points"])).double()
     mod.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
-    mod = mod.to("cuda", dtype)
+    mod = mod.to("cuda", dtype)  # (parameters are loaded in fp64 first so the fp64 run sees the exact golden weights)
     cu = lambda k: torch.from_numpy(g[k]).to("cuda")
     query = cu("query").to(dtype).requires_grad_(True)
     src = cu("input_flatten").to(dtype).requires_grad_(True)
