@@ -10,7 +10,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "msda_kernels_v2.cuh"
+#include "msda_kernels_v3.cuh"
 
 #include <atomic>
 
@@ -67,9 +67,11 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 constexpr int kWarps = 8;
 
 // Process-wide tuning knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/).
-std::atomic<int> g_variant{2};     // 1: first-generation kernels, 2: resolve-once kernels
+std::atomic<int> g_variant{2};     // 1 | 2 | 3 | 4 select a kernel generation (2 = measured best); 0 = auto by size
+std::atomic<int> g_v3_threads{1024};  // v3 CTA size: 512 or 1024
+std::atomic<int> g_v3_min_rows{256};  // auto mode: v3 when M*Lq / #SMs >= this
 std::atomic<int> g_head_major{0};  // v2 only: 0 = rows in memory order (b,q,m), 1 = (b,m,q)
-std::atomic<int> g_warps{8};       // v2 warps per CTA for the flagship specialisation: 4, 8 or 16
+std::atomic<int> g_warps{4};       // v2 warps per CTA for the flagship specialisation: 4, 8 or 16
 
 struct Geometry {
     int64_t rows;
@@ -182,6 +184,32 @@ void bwd_v2_launch(const msda_dims *d, int64_t rows, const void *value, const in
              HM ? "head-major" : "row-major");
 }
 
+template <typename T, int DD, int LL, int PP, int W>
+int fwd_v2p_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
+                   const void *loc, const void *attn, void *out, cudaStream_t st)
+{
+    auto kernel = msda::msda_fwd_v2p<T, DD, LL, PP, W>;
+    thread_local int blocks_per_sm = 0;
+    thread_local int sms = 0;
+    if (blocks_per_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, W * 32, 0) != cudaSuccess ||
+            blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    int64_t grid = (int64_t)sms * blocks_per_sm;
+    const int64_t need = (rows + W - 1) / W;
+    if (grid > need) grid = need;
+    kernel<<<(unsigned)grid, W * 32, 0, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+                                              (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query,
+                                              rows);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v2p<%s,D%d,L%d,P%d,w%d,persistent x%d>", tname<T>(), DD, LL, PP, W,
+             blocks_per_sm);
+    return MSDA_OK;
+}
+
 template <int DD, int LL, int PP, int E>
 constexpr bool v2_ok()
 {
@@ -254,6 +282,114 @@ bool launch_bwd_v2(const msda_dims *d, const Geometry &g, const void *value, con
     return false;
 }
 
+// ---- v3: persistent CTAs with shared-memory staging ------------------------------------------------
+struct DeviceInfo {
+    int sms = 0;
+    int max_smem_optin = 0;
+};
+
+const DeviceInfo &device_info()
+{
+    thread_local DeviceInfo cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceInfo &d = cache[dev & 63];
+    if (d.sms == 0) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return d;
+}
+
+bool v3_wanted(const msda_dims *d)
+{
+    const int v = g_variant.load();
+    if (v == 3) return true;
+    if (v != 0) return false;
+    const DeviceInfo &di = device_info();
+    return di.sms > 0 && d->num_heads * d->num_query / di.sms >= g_v3_min_rows.load();
+}
+
+template <typename K>
+int v3_prepare(K kernel, int *smem_bytes)
+{
+    const DeviceInfo &di = device_info();
+    *smem_bytes = di.max_smem_optin - 1024;  // leave room for the kernel's static shared memory
+    if (*smem_bytes <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes),
+                      "cudaFuncSetAttribute(v3)");
+}
+
+template <typename T, int DD, int LL, int PP, int TH>
+int fwd_v3_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                  const void *attn, void *out, cudaStream_t st)
+{
+    auto kernel = msda::msda_fwd_v3<T, DD, LL, PP, TH>;
+    int smem = 0;
+    if (int rc = v3_prepare(kernel, &smem)) return rc;
+    kernel<<<device_info().sms, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc,
+                                                (const float *)attn, (T *)out, (int)d->batch, (int)d->spatial_size,
+                                                (int)d->num_heads, (int)d->num_query, smem / (int)sizeof(T));
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v3<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
+    return MSDA_OK;
+}
+
+template <typename T, int DD, int LL, int PP, int TH>
+int bwd_v3_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                  const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    auto kernel = msda::msda_bwd_v3<T, DD, LL, PP, TH>;
+    int smem = 0;
+    if (int rc = v3_prepare(kernel, &smem)) return rc;
+    kernel<<<device_info().sms, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc,
+                                                (const float *)attn, (const T *)gout, gv_acc, (float *)gloc,
+                                                (float *)gattn, (int)d->batch, (int)d->spatial_size,
+                                                (int)d->num_heads, (int)d->num_query, smem / (int)sizeof(float));
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v3<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
+    return MSDA_OK;
+}
+
+#define MSDA_FOR_EACH_V3_SPEC(X) \
+    X(32, 4, 4)                  \
+    X(64, 4, 4)
+
+// returns -1 when no v3 specialisation matches, else a status code
+template <typename T>
+int launch_fwd_v3(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                  const void *attn, void *out, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+    const bool big = g_v3_threads.load() >= 1024;
+#define X(DD, LL, PP)                                                                                     \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                               \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                        \
+            return big ? fwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, out, st)    \
+                       : fwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, out, st);    \
+    }
+    MSDA_FOR_EACH_V3_SPEC(X)
+#undef X
+    return -1;
+}
+
+template <typename T>
+int launch_bwd_v3(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                  const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+    const bool big = g_v3_threads.load() >= 1024;
+#define X(DD, LL, PP)                                                                                                \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                          \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                                   \
+            return big ? bwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc,    \
+                                                            gattn, st)                                               \
+                       : bwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc,     \
+                                                           gattn, st);                                               \
+    }
+    MSDA_FOR_EACH_V3_SPEC(X)
+#undef X
+    return -1;
+}
+
 template <typename T, typename C>
 void launch_fwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
                         const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st,
@@ -295,6 +431,8 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "variant")) knob = &g_variant;
     if (key && !strcmp(key, "head_major")) knob = &g_head_major;
     if (key && !strcmp(key, "warps")) knob = &g_warps;
+    if (key && !strcmp(key, "v3_threads")) knob = &g_v3_threads;
+    if (key && !strcmp(key, "v3_min_rows")) knob = &g_v3_min_rows;
     if (!knob) return -1;
     return knob->exchange(value);
 }
@@ -323,7 +461,30 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        if (g_variant.load() == 2) {
+        if (v3_wanted(dims) && dims->batch < (1 << 30) && dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
+            const int rc = dtype == MSDA_F32
+                               ? launch_fwd_v3<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                      attn_weight, output, st)
+                               : launch_fwd_v3<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
+                                                              sampling_loc, attn_weight, output, st);
+            if (rc > 0) return rc;
+            done = rc == 0;
+        }
+        if (!done && g_variant.load() == 4 && dims->channels == 32 && dims->num_levels == 4 && dims->num_point == 4 &&
+            dtype == MSDA_F32) {
+            const int w = g_warps.load();
+            if (w == 4)
+                fwd_v2p_launch<float, 32, 4, 4, 4>(dims, g.rows, value, spatial_shapes, level_start_index,
+                                                   sampling_loc, attn_weight, output, st);
+            else if (w == 16)
+                fwd_v2p_launch<float, 32, 4, 4, 16>(dims, g.rows, value, spatial_shapes, level_start_index,
+                                                    sampling_loc, attn_weight, output, st);
+            else
+                fwd_v2p_launch<float, 32, 4, 4, 8>(dims, g.rows, value, spatial_shapes, level_start_index,
+                                                   sampling_loc, attn_weight, output, st);
+            done = true;
+        }
+        if (!done && g_variant.load() != 1) {
             done = dtype == MSDA_F32 ? launch_fwd_v2<float>(dims, g, value, spatial_shapes, level_start_index,
                                                            sampling_loc, attn_weight, output, st)
                                      : launch_fwd_v2<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index,
@@ -403,7 +564,18 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) && aligned16(gv_acc) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
         (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0) {
-        if (g_variant.load() == 2) {
+        if (v3_wanted(dims) && dims->batch < (1 << 30) && dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
+            const int rc =
+                dtype == MSDA_F32
+                    ? launch_bwd_v3<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                           grad_output, (float *)gv_acc, grad_sampling_loc, grad_attn_weight, st)
+                    : launch_bwd_v3<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                   attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                   grad_attn_weight, st);
+            if (rc > 0) return rc;
+            done = rc == 0;
+        }
+        if (!done && g_variant.load() != 1) {
             done = dtype == MSDA_F32
                        ? launch_bwd_v2<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
                                               attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,

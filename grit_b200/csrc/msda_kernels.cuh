@@ -41,6 +41,11 @@ struct Chunk<float> {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
         r[0] = v.x, r[1] = v.y, r[2] = v.z, r[3] = v.w;
     }
+    __device__ __forceinline__ static void load_shared(const float *p, float (&r)[4])
+    {
+        const float4 v = *reinterpret_cast<const float4 *>(p);
+        r[0] = v.x, r[1] = v.y, r[2] = v.z, r[3] = v.w;
+    }
     __device__ __forceinline__ static void store(float *p, const float (&r)[4])
     {
         *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
@@ -50,15 +55,22 @@ struct Chunk<float> {
 template <>
 struct Chunk<__nv_bfloat16> {
     static constexpr int E = 8;
-    __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&r)[8])
+    __device__ __forceinline__ static void unpack(const uint4 &v, float (&r)[8])
     {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
         const unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             r[2 * i] = __uint_as_float(w[i] << 16);
             r[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
         }
+    }
+    __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&r)[8])
+    {
+        unpack(__ldg(reinterpret_cast<const uint4 *>(p)), r);
+    }
+    __device__ __forceinline__ static void load_shared(const __nv_bfloat16 *p, float (&r)[8])
+    {
+        unpack(*reinterpret_cast<const uint4 *>(p), r);
     }
     __device__ __forceinline__ static void store(__nv_bfloat16 *p, const float (&r)[8])
     {

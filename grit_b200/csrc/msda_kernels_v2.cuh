@@ -34,6 +34,18 @@ __device__ __forceinline__ Resolved resolve_point(float x, float y, int H, int W
     return r;
 }
 
+// same, with the attention weight already in a register (software-prefetched by the persistent kernels)
+__device__ __forceinline__ Resolved resolve_point_v(float x, float y, int H, int W, int start, float attn_raw)
+{
+    const Taps t = resolve_taps(x, y, H, W, start);
+    Resolved r;
+    const int mask = (t.tl ? 1 : 0) | (t.tr ? 2 : 0) | (t.bl ? 4 : 0) | (t.br ? 8 : 0);
+    r.pm = t.pix * 16 + mask;
+    r.a = t.live ? attn_raw : 0.f;  // a skipped point ignores its weight (NaN included), like the reference
+    r.lh = t.lh, r.lw = t.lw;
+    return r;
+}
+
 template <bool HEAD_MAJOR>
 __device__ __forceinline__ void decode_row(unsigned urow, int M, int Lq, int64_t &b, int &m, int64_t &row)
 {
@@ -116,6 +128,90 @@ msda_fwd_v2(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
         for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
     }
     if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+}
+
+// Persistent flavour of msda_fwd_v2: a fixed grid of resident warps strides over the rows in memory order
+// and keeps the NEXT row's location / weight loads in flight while the current row gathers, so the DRAM
+// latency of the loc/attn stream is off the critical path and no CTA-launch overhead is paid per 4-8 rows.
+template <typename T, int D, int L, int P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+msda_fwd_v2p(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int M, int Lq,
+             int64_t rows)
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    constexpr int PPG = LP / G;
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+
+    __shared__ int sH[L], sW[L], sStart[L];
+    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPT, sub = lane % LPT;
+    const unsigned stride = gridDim.x * WARPS;
+    const int MD = M * D;
+    const int rp = lane % LP;
+    const int rl = rp / P;
+    const int rH = sH[rl], rW = sW[rl], rStart = sStart[rl];
+    int pitch[PPG];
+#pragma unroll
+    for (int it = 0; it < PPG; ++it) pitch[it] = sW[(it * G + g) / P] * MD;
+
+    unsigned urow = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    float2 xy_next = make_float2(0.f, 0.f);
+    float a_next = 0.f;
+    if (urow < (unsigned)rows) {
+        xy_next = __ldg(reinterpret_cast<const float2 *>(loc) + (int64_t)urow * LP + rp);
+        a_next = __ldg(attn + (int64_t)urow * LP + rp);
+    }
+    for (; urow < (unsigned)rows; urow += stride) {
+        const int64_t row = urow;
+        const float2 xy = xy_next;
+        const float a_raw = a_next;
+        if (urow + stride < (unsigned)rows) {
+            xy_next = __ldg(reinterpret_cast<const float2 *>(loc) + (row + stride) * LP + rp);
+            a_next = __ldg(attn + (row + stride) * LP + rp);
+        }
+        const int m = (int)(urow % (unsigned)M);
+        const int64_t b = urow / ((unsigned)M * (unsigned)Lq);
+        const T *vimg = value + (b * S * M + m) * (int64_t)D + sub * E;
+        const Resolved mine = resolve_point_v(xy.x, xy.y, rH, rW, rStart, a_raw);
+
+        float acc[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] = 0.f;
+#pragma unroll
+        for (int it = 0; it < PPG; ++it) {
+            const int pt = it * G + g;
+            const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+            const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+            const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+            const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+            const T *p0 = vimg + (int64_t)(pm >> 4) * MD;
+            const T *p1 = p0 + pitch[it];
+            float v0[E], v1[E], v2[E], v3[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+            if (pm & 1) Chunk<T>::load(p0, v0);
+            if (pm & 2) Chunk<T>::load(p0 + MD, v1);
+            if (pm & 4) Chunk<T>::load(p1, v2);
+            if (pm & 8) Chunk<T>::load(p1 + MD, v3);
+            const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+            const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+        }
+#pragma unroll
+        for (int off = LPT; off < 32; off <<= 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+        }
+        if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+    }
 }
 
 // Halving reduction of NV = 3*PPG values over the LPT lanes of a group.  On return lane `sub` holds, in

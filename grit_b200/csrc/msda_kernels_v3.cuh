@@ -1,0 +1,344 @@
+// msda_kernels_v3.cuh -- persistent, shared-memory-staged kernels for large query counts (sm_100a).
+//
+// Why: the first two kernel generations are bound by the SM <-> L2 crossbar, not by HBM
+// (profiles/r01_*.txt): every bilinear tap is a 128-byte line that misses L1, and in the backward
+// every tap is a 128-byte `red` that has to leave the SM (L1->XBAR request path 90 % busy).
+// The coarse pyramid levels of ONE (image, head) pair are tiny, though -- at 800x1333 levels 2+3
+// are 1323 pixels = 169 KB in fp32 -- and receive half of all taps.  So:
+//
+//   * one persistent CTA per SM; the CTAs sweep the batch one image at a time (keeps the image's
+//     value maps L2-resident), each CTA owning a contiguous slice of the image's (head, query)
+//     rows in head-major order, i.e. at most two (image, head) segments per image;
+//   * per segment the CTA stages the head's coarse-level planes in shared memory
+//       forward : the VALUE planes  -> taps on staged levels are LDS.128, not L2 round trips;
+//       backward: fp32 grad_value ACCUMULATORS -> taps on staged levels are shared-memory atomics,
+//                 flushed with one vector `red` per pixel when the segment ends;
+//     which levels fit is decided on the device from spatial_shapes (no host sync): greedy from
+//     the smallest plane up, within the dynamic shared-memory budget passed at launch;
+//   * rows are processed exactly like v2 (warp per row, resolve once, lane group per tap).
+#pragma once
+
+#include "msda_kernels_v2.cuh"
+
+namespace msda {
+
+constexpr int kV3MaxLevels = 8;
+
+struct V3Plan {
+    int H[kV3MaxLevels], W[kV3MaxLevels], start[kV3MaxLevels];
+    int sbase[kV3MaxLevels];  // element offset of pixel `start[l]`... see plan_levels(); INT_MIN/2 when not staged
+    int soff[kV3MaxLevels];   // element offset of the level's plane inside the staging buffer, -1 when not staged
+    int staged_elems;         // total staged elements (D per pixel)
+};
+
+constexpr int kNotStaged = -(1 << 30);
+
+// Thread 0 decides which levels live in shared memory: smallest planes first while they fit.
+template <int L, int D>
+__device__ __forceinline__ void plan_levels(const int64_t *shapes, const int64_t *lsi, int budget_elems, V3Plan &plan)
+{
+    if (threadIdx.x == 0) {
+        int order[L];
+        for (int l = 0; l < L; ++l) {
+            plan.H[l] = (int)shapes[2 * l];
+            plan.W[l] = (int)shapes[2 * l + 1];
+            plan.start[l] = (int)lsi[l];
+            plan.soff[l] = -1;
+            plan.sbase[l] = kNotStaged;
+            order[l] = l;
+        }
+        for (int i = 1; i < L; ++i)  // insertion sort by plane size
+            for (int j = i; j > 0 && plan.H[order[j]] * plan.W[order[j]] < plan.H[order[j - 1]] * plan.W[order[j - 1]]; --j) {
+                const int t = order[j];
+                order[j] = order[j - 1];
+                order[j - 1] = t;
+            }
+        int used = 0;
+        for (int i = 0; i < L; ++i) {
+            const int l = order[i];
+            const long long need = (long long)plan.H[l] * plan.W[l] * D;
+            if (need > 0 && used + need <= budget_elems) {
+                plan.soff[l] = used;
+                plan.sbase[l] = used - plan.start[l] * D;  // smem element index of image pixel p is sbase + p*D
+                used += (int)need;
+            }
+        }
+        plan.staged_elems = used;
+    }
+    __syncthreads();
+}
+
+// Row range of CTA `c` inside one image, in head-major order (row index = m*Lq + q).
+__device__ __forceinline__ void cta_slice(int c, int nctas, int M, int Lq, int &lo, int &hi)
+{
+    const long long R = (long long)M * Lq;
+    lo = (int)(R * c / nctas);
+    hi = (int)(R * (c + 1) / nctas);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <typename T, int D, int L, int P, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+            const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int N, int S, int M,
+            int Lq, int budget_elems)
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    constexpr int PPG = LP / G;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(L <= kV3MaxLevels && LP <= 32 && 32 % LP == 0 && LP % G == 0, "unsupported");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *stage = reinterpret_cast<T *>(smem_raw);
+    __shared__ V3Plan plan;
+    plan_levels<L, D>(shapes, lsi, budget_elems, plan);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPT, sub = lane % LPT;
+    const int MD = M * D;
+    int lo, hi;
+    cta_slice(blockIdx.x, gridDim.x, M, Lq, lo, hi);
+    if (lo >= hi) return;
+    const int rp = lane % LP, rl = rp / P;
+    const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
+
+    for (int b = 0; b < N; ++b) {
+        for (int m = lo / Lq; m <= (hi - 1) / Lq; ++m) {
+            const int q0 = max(lo - m * Lq, 0), q1 = min(hi - m * Lq, Lq);
+            const T *vimg = value + ((int64_t)b * S * M + m) * D;
+
+            // ---- stage this head's coarse planes ---------------------------------------------------
+            __syncthreads();  // previous segment's readers are done
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int so = plan.soff[l];
+                if (so < 0) continue;
+                const int chunks = plan.H[l] * plan.W[l] * LPT;
+                const T *src = vimg + (int64_t)plan.start[l] * MD;
+                for (int i = threadIdx.x; i < chunks; i += THREADS) {
+                    const int pix = i / LPT, ch = i % LPT;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (int64_t)pix * MD + ch * E));
+                    *reinterpret_cast<uint4 *>(stage + so + pix * D + ch * E) = v;
+                }
+            }
+            __syncthreads();
+
+            // ---- rows of this segment ---------------------------------------------------------------
+            // software pipeline: the next row's location / weight are in flight while this row gathers
+            float2 xy_next = make_float2(0.f, 0.f);
+            float a_next = 0.f;
+            if (q0 + warp < q1) {
+                const int64_t r0 = ((int64_t)b * Lq + q0 + warp) * M + m;
+                xy_next = __ldg(reinterpret_cast<const float2 *>(loc) + r0 * LP + rp);
+                a_next = __ldg(attn + r0 * LP + rp);
+            }
+            for (int q = q0 + warp; q < q1; q += WARPS) {
+                const int64_t row = ((int64_t)b * Lq + q) * M + m;
+                const float2 xy = xy_next;
+                const float a_raw = a_next;
+                if (q + WARPS < q1) {
+                    const int64_t rn = row + (int64_t)WARPS * M;
+                    xy_next = __ldg(reinterpret_cast<const float2 *>(loc) + rn * LP + rp);
+                    a_next = __ldg(attn + rn * LP + rp);
+                }
+                const Resolved mine = resolve_point_v(xy.x, xy.y, rH, rW, rStart, a_raw);
+                float acc[E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) acc[e] = 0.f;
+#pragma unroll
+                for (int it = 0; it < PPG; ++it) {
+                    const int pt = it * G + g;
+                    const int l = pt / P;
+                    const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+                    const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+                    const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+                    const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+                    const int W = plan.W[l];
+                    const int sb = plan.sbase[l];
+                    const int pix = pm >> 4;
+                    float v0[E], v1[E], v2[E], v3[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+                    if (sb != kNotStaged) {
+                        const T *s0 = stage + sb + pix * D + sub * E;
+                        const T *s1 = s0 + W * D;
+                        if (pm & 1) Chunk<T>::load_shared(s0, v0);
+                        if (pm & 2) Chunk<T>::load_shared(s0 + D, v1);
+                        if (pm & 4) Chunk<T>::load_shared(s1, v2);
+                        if (pm & 8) Chunk<T>::load_shared(s1 + D, v3);
+                    } else {
+                        const T *p0 = vimg + (int64_t)pix * MD + sub * E;
+                        const T *p1 = p0 + (int64_t)W * MD;
+                        if (pm & 1) Chunk<T>::load(p0, v0);
+                        if (pm & 2) Chunk<T>::load(p0 + MD, v1);
+                        if (pm & 4) Chunk<T>::load(p1, v2);
+                        if (pm & 8) Chunk<T>::load(p1 + MD, v3);
+                    }
+                    const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+                    const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+                }
+#pragma unroll
+                for (int off = LPT; off < 32; off <<= 1) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+                }
+                if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// shared-memory fp32 accumulate of this lane's E channels of one tap.  Element order is rotated by the lane
+// group so the G groups of a warp hit disjoint bank sets (a tap is D consecutive floats = banks sub*E+j).
+template <int E>
+__device__ __forceinline__ void smem_add_chunk(float *p, const float (&go)[E], float s, int rot)
+{
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const int k = (j + rot) % E;
+        float x = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) x = (e == k) ? go[e] : x;  // register select (no dynamic indexing)
+        atomicAdd(p + k, s * x);
+    }
+}
+
+template <typename T, int D, int L, int P, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+msda_bwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+            const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
+            float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int N, int S,
+            int M, int Lq, int budget_elems)
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    constexpr int PPG = LP / G;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(L <= kV3MaxLevels && LP <= 32 && 32 % LP == 0 && LP % G == 0, "unsupported");
+    static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *acc_s = reinterpret_cast<float *>(smem_raw);
+    __shared__ V3Plan plan;
+    plan_levels<L, D>(shapes, lsi, budget_elems, plan);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPT, sub = lane % LPT;
+    const int MD = M * D;
+    int lo, hi;
+    cta_slice(blockIdx.x, gridDim.x, M, Lq, lo, hi);
+    if (lo >= hi) return;
+    const int rp = lane % LP, rl = rp / P;
+    const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
+    const int staged4 = plan.staged_elems / 4;
+
+    for (int i = threadIdx.x; i < staged4; i += THREADS)
+        reinterpret_cast<float4 *>(acc_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int b = 0; b < N; ++b) {
+        for (int m = lo / Lq; m <= (hi - 1) / Lq; ++m) {
+            const int q0 = max(lo - m * Lq, 0), q1 = min(hi - m * Lq, Lq);
+            const int64_t img = ((int64_t)b * S * M + m) * D;
+            const T *vimg = value + img;
+            float *gimg = gv_acc + img;
+            __syncthreads();  // accumulators are zero (initial fill or previous flush)
+
+            for (int q = q0 + warp; q < q1; q += WARPS) {
+                const int64_t row = ((int64_t)b * Lq + q) * M + m;
+                const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + row * LP + rp);
+                const Resolved mine = resolve_point(xy.x, xy.y, rH, rW, rStart, attn + row * LP + rp);
+                float go[E];
+                Chunk<T>::load(grad_out + row * D + sub * E, go);
+                float part[3 * PPG];
+#pragma unroll
+                for (int it = 0; it < PPG; ++it) {
+                    const int pt = it * G + g;
+                    const int l = pt / P;
+                    const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+                    const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+                    const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+                    const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+                    const int W = plan.W[l];
+                    const int sb = plan.sbase[l];
+                    const int pix = pm >> 4;
+                    const int64_t o0 = (int64_t)pix * MD + sub * E, o1 = o0 + (int64_t)W * MD;
+                    float v0[E], v1[E], v2[E], v3[E];
+#pragma unroll
+                    for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+                    if (pm & 1) Chunk<T>::load(vimg + o0, v0);
+                    if (pm & 2) Chunk<T>::load(vimg + o0 + MD, v1);
+                    if (pm & 4) Chunk<T>::load(vimg + o1, v2);
+                    if (pm & 8) Chunk<T>::load(vimg + o1 + MD, v3);
+                    const float hh = 1.f - lh, hw = 1.f - lw;
+                    const float ah = a * hh, al = a * lh;
+                    if (sb != kNotStaged) {
+                        float *s0 = acc_s + sb + pix * D + sub * E;
+                        float *s1 = s0 + W * D;
+                        if (pm & 1) smem_add_chunk<E>(s0, go, ah * hw, g);
+                        if (pm & 2) smem_add_chunk<E>(s0 + D, go, ah * lw, g);
+                        if (pm & 4) smem_add_chunk<E>(s1, go, al * hw, g);
+                        if (pm & 8) smem_add_chunk<E>(s1 + D, go, al * lw, g);
+                    } else {
+                        if (pm & 1) red_add_chunk<E>(gimg + o0, go, ah * hw);
+                        if (pm & 2) red_add_chunk<E>(gimg + o0 + MD, go, ah * lw);
+                        if (pm & 4) red_add_chunk<E>(gimg + o1, go, al * hw);
+                        if (pm & 8) red_add_chunk<E>(gimg + o1 + MD, go, al * lw);
+                    }
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        d0 = fmaf(go[e], v0[e], d0);
+                        d1 = fmaf(go[e], v1[e], d1);
+                        d2 = fmaf(go[e], v2[e], d2);
+                        d3 = fmaf(go[e], v3[e], d3);
+                    }
+                    part[3 * it + 0] = hh * (hw * d0 + lw * d1) + lh * (hw * d2 + lw * d3);
+                    part[3 * it + 1] = a * (hh * (d1 - d0) + lh * (d3 - d2));
+                    part[3 * it + 2] = a * (hw * (d2 - d0) + lw * (d3 - d1));
+                }
+                group_reduce3<PPG, LPT>(part, sub);
+                constexpr int SPAN = LPT / PPG;
+                if (sub % SPAN == 0) {
+                    const int pt = (sub / SPAN) * G + g;
+                    const int l = pt / P;
+                    reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] =
+                        make_float2((float)plan.W[l] * part[1], (float)plan.H[l] * part[2]);
+                    grad_attn[row * LP + pt] = part[0];
+                }
+            }
+
+            // ---- flush the staged accumulators into grad_value and re-zero them ------------------------
+            __syncthreads();
+#pragma unroll
+            for (int l = 0; l < L; ++l) {
+                const int so = plan.soff[l];
+                if (so < 0) continue;
+                const int quads = plan.H[l] * plan.W[l] * (D / 4);
+                float *dst = gimg + (int64_t)plan.start[l] * MD;
+                for (int i = threadIdx.x; i < quads; i += THREADS) {
+                    const int pix = i / (D / 4), c4 = i % (D / 4);
+                    float4 *sp = reinterpret_cast<float4 *>(acc_s + so + pix * D) + c4;
+                    const float4 v = *sp;
+                    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
+                        red_add_f32x4(dst + (int64_t)pix * MD + c4 * 4, v.x, v.y, v.z, v.w);
+                    *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace msda

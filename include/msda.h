@@ -87,7 +87,11 @@ const char *msda_last_kernel(void);
 /* Kernel launches enqueued by this thread since the counter was last reset (memsets excluded). */
 int64_t msda_launch_count(int reset);
 
-/* Tuning / A-B testing knob (process-wide).  Keys: "variant" (1 | 2), "head_major" (0 | 1), "warps" (4 | 8 | 16).
+/* Tuning / A-B testing knob (process-wide).  Keys:
+ *   "variant"     1 first-generation kernels | 2 resolve-once kernels (default) | 3 persistent shared-memory-staged
+ *                 kernels | 4 persistent forward with software prefetch | 0 choose 3 or 2 by problem size
+ *   "head_major"  0 | 1   (variant 2: row order)        "warps"  4 | 8 | 16  (variant 2/4: warps per CTA, D=32 L=P=4)
+ *   "v3_threads"  512 | 1024                             "v3_min_rows"  threshold of the size heuristic
  * Returns the previous value, or -1 for an unknown key.  Results do not depend on the knobs beyond fp rounding. */
 int msda_set_tuning(const char *key, int value);
 

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--loc-dist", default="uniform")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--sets", type=int, default=3)
-    ap.add_argument("--configs", default="1:0:8,2:0:8,2:1:8,2:0:4,2:1:4,2:0:16,2:1:16")
+    ap.add_argument("--configs", default="2:0:4,3:0:512,3:0:1024")
     args = ap.parse_args()
     cfg = bench.WORKLOADS[args.workload]
     dev = torch.device("cuda:0")
@@ -44,7 +44,8 @@ def main():
     print(f"{'variant:hm:warps':18s} {'fwd ms':>8s} {'frac':>6s} {'bwd ms':>8s} {'frac':>6s} {'Mq/s f+b':>9s}  kernels / max err vs first config")
     for spec in args.configs.split(","):
         variant, hm, warps = (int(x) for x in spec.split(":"))
-        _lib.set_tuning("variant", variant), _lib.set_tuning("head_major", hm), _lib.set_tuning("warps", warps)
+        _lib.set_tuning("variant", variant), _lib.set_tuning("head_major", hm)
+        _lib.set_tuning("v3_threads" if variant == 3 else "warps", warps)
         s = sets[0]
         out = _lib.forward(s["value"], shapes, lsi, s["loc"], s["attn"])
         kf = _lib.last_kernel()

@@ -109,30 +109,34 @@ def test_reference_gradcheck(lib, channels):
 
 SMALL_PYR = [(12, 20), (6, 10), (3, 5), (2, 3)]
 RANDOM_CASES = [
-    # N, Lq,  M, D,   shapes,                         P, expected forward kernel for fp32
-    (2, 37, 8, 32, SMALL_PYR, 4, "fwd_vec<f32,D32,L4,P4>"),
-    (2, 19, 8, 64, SMALL_PYR, 4, "fwd_vec<f32,D64,L4,P4>"),
-    (1, 23, 4, 16, SMALL_PYR, 4, "fwd_vec<f32,D16,L4,P4>"),
-    (1, 11, 2, 128, SMALL_PYR, 4, "fwd_vec<f32,D128,L4,P4>"),
-    (2, 13, 8, 32, SMALL_PYR, 8, "fwd_vec<f32,D32,L4,P8>"),
-    (2, 29, 8, 32, [(9, 14)], 4, "fwd_vec<f32,D32,L1,P4>"),
-    (2, 17, 3, 5, [(5, 7), (1, 1), (2, 3)], 2, "fwd_generic<f32>"),
-    (1, 9, 2, 71, [(4, 4), (2, 2)], 3, "fwd_generic<f32>"),
-    (3, 5, 8, 32, [(7, 9), (4, 5), (2, 3)], 4, "fwd_generic<f32>"),
-    (1, 6, 1, 40, [(3, 1), (1, 5)], 1, "fwd_generic<f32>"),
+    # N, Lq,  M, D,   shapes,                         P, specialised kernel expected for fp32?
+    (2, 37, 8, 32, SMALL_PYR, 4, True),
+    (2, 19, 8, 64, SMALL_PYR, 4, True),
+    (1, 23, 4, 16, SMALL_PYR, 4, True),
+    (1, 11, 2, 128, SMALL_PYR, 4, True),
+    (2, 13, 8, 32, SMALL_PYR, 8, True),
+    (2, 29, 8, 32, [(9, 14)], 4, True),
+    (2, 17, 3, 5, [(5, 7), (1, 1), (2, 3)], 2, False),
+    (1, 9, 2, 71, [(4, 4), (2, 2)], 3, False),
+    (3, 5, 8, 32, [(7, 9), (4, 5), (2, 3)], 4, False),
+    (1, 6, 1, 40, [(3, 1), (1, 5)], 1, False),
 ]
+
+
+def is_specialised(kernel_name):
+    return not kernel_name.split("<")[0].endswith("generic")
 
 
 @pytest.mark.parametrize("spec", RANDOM_CASES, ids=lambda s: f"N{s[0]}Lq{s[1]}M{s[2]}D{s[3]}L{len(s[4])}P{s[5]}")
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32, torch.bfloat16])
 def test_random_problems_vs_oracle(lib, oracle, spec, dtype):
-    N, Lq, M, D, shapes, P, kernel = spec
+    N, Lq, M, D, shapes, P, fast = spec
     case = helpers.rounded_case(helpers.make_inputs(N, Lq, M, D, shapes, P, seed=hash((N, Lq, D, P)) % 1000,
                                                     lo=-0.2, hi=1.2), dtype)
     got = run_kernels(lib, case, dtype)
     if dtype == torch.float32:
-        assert got["fwd_kernel"] == kernel
-        assert got["bwd_kernel"] == kernel.replace("fwd", "bwd")
+        assert is_specialised(got["fwd_kernel"]) == fast, got["fwd_kernel"]
+        assert is_specialised(got["bwd_kernel"]) == fast, got["bwd_kernel"]
     if dtype == torch.float64:
         assert got["fwd_kernel"] == "fwd_generic<f64>"
     assert_parity(got, oracle_results(oracle, case), case, dtype, str(spec[:4]))
@@ -143,10 +147,38 @@ def test_specialised_and_generic_kernels_agree(lib, oracle, dtype):
     case = helpers.rounded_case(helpers.make_inputs(2, 50, 8, 32, SMALL_PYR, 4, seed=5), dtype)
     fast = run_kernels(lib, case, dtype)
     slow = run_kernels(lib, case, dtype, flags=lib.FLAG_FORCE_GENERIC)
-    assert fast["fwd_kernel"].startswith("fwd_vec") and slow["fwd_kernel"].startswith("fwd_generic")
+    assert is_specialised(fast["fwd_kernel"]) and not is_specialised(slow["fwd_kernel"])
     ref = oracle_results(oracle, case)
-    assert_parity(fast, ref, case, dtype, "vec")
+    assert_parity(fast, ref, case, dtype, "specialised")
     assert_parity(slow, ref, case, dtype, "generic")
+
+
+KERNEL_GENERATIONS = [  # (msda_set_tuning settings, expected kernel-name prefix)
+    ({"variant": 1}, "vec"),
+    ({"variant": 2, "head_major": 0, "warps": 4}, "v2"),
+    ({"variant": 2, "head_major": 1, "warps": 8}, "v2"),
+    ({"variant": 2, "head_major": 0, "warps": 16}, "v2"),
+    ({"variant": 3, "v3_threads": 512}, "v3"),
+    ({"variant": 3, "v3_threads": 1024}, "v3"),
+    ({"variant": 4, "warps": 8}, "v2"),
+]
+
+
+@pytest.mark.parametrize("tuning,prefix", KERNEL_GENERATIONS, ids=lambda t: str(t))
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 64), (torch.bfloat16, 32), (torch.bfloat16, 64)])
+def test_every_kernel_generation_matches_oracle(lib, oracle, tuning, prefix, dtype, D):
+    """All selectable kernel generations (A/B knobs of include/msda.h) compute the same function.  The pyramid is
+    big enough that the shared-memory-staged generation stages some levels and leaves others in global memory."""
+    shapes = [(40, 60), (20, 30), (10, 15), (5, 8)]
+    case = helpers.rounded_case(helpers.make_inputs(2, 301, 8, D, shapes, 4, seed=17, lo=-0.1, hi=1.1), dtype)
+    saved = {k: lib.set_tuning(k, v) for k, v in tuning.items()}
+    try:
+        got = run_kernels(lib, case, dtype)
+    finally:
+        for k, v in saved.items():
+            lib.set_tuning(k, v)
+    assert prefix in got["bwd_kernel"], got["bwd_kernel"]
+    assert_parity(got, oracle_results(oracle, case), case, dtype, str(tuning))
 
 
 def test_edge_cases(lib, oracle):
@@ -238,7 +270,7 @@ def test_full_size_sample_rows_vs_oracle(lib, oracle):
     case = helpers.make_inputs(N, 4096, M, D, shapes_l, P, seed=3, dtype=np.float32)
     case = helpers.rounded_case(case, torch.float32)
     got = run_kernels(lib, case, torch.float32)
-    assert got["fwd_kernel"] == "fwd_vec<f32,D32,L4,P4>"
+    assert is_specialised(got["fwd_kernel"]) and is_specialised(got["bwd_kernel"])
     assert_parity(got, oracle_results(oracle, case), case, torch.float32, "800x1333")
 
 
