@@ -39,6 +39,12 @@ WORKLOADS = {
                                  dtype="f32", layers=6),
     "grit_decoder_384x640_bf16": dict(N=64, shapes=[(48, 80), (24, 40), (12, 20), (6, 10)], Lq=150, M=8, D=64, P=4,
                                       dtype="bf16", layers=6),
+    "detr_encoder_800x1333_bf16": dict(N=32, shapes=[(100, 167), (50, 84), (25, 42), (13, 21)], Lq=None, M=8, D=32, P=4,
+                                       dtype="bf16", layers=6),
+    "detr_encoder_800x1333_d64": dict(N=8, shapes=[(100, 167), (50, 84), (25, 42), (13, 21)], Lq=None, M=8, D=64, P=4,
+                                      dtype="f32", layers=6),
+    "grit_decoder_800x1333_bf16": dict(N=32, shapes=[(100, 167), (50, 84), (25, 42), (13, 21)], Lq=150, M=8, D=64, P=4,
+                                       dtype="bf16", layers=6),
     "tiny": dict(N=2, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], Lq=None, M=8, D=32, P=4, dtype="f32", layers=2),
 }
 OP_PARAMS_PER_LAYER = {256: 230272, 512: 722304}  # the four Linears of one MSDeformAttn

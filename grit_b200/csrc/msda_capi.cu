@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "msda_kernels_v3.cuh"
+#include "msda_kernels_v5.cuh"
 
 #include <atomic>
 
@@ -67,7 +68,7 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 constexpr int kWarps = 8;
 
 // Process-wide tuning knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/).
-std::atomic<int> g_variant{2};     // 1 | 2 | 3 | 4 select a kernel generation (2 = measured best); 0 = auto by size
+std::atomic<int> g_variant{5};     // 1 | 2 | 3 | 4 | 5 select a kernel generation (5 = measured best); 0 = auto by size
 std::atomic<int> g_v3_threads{1024};  // v3 CTA size: 512 or 1024
 std::atomic<int> g_v3_min_rows{256};  // auto mode: v3 when M*Lq / #SMs >= this
 std::atomic<int> g_head_major{0};  // v2 only: 0 = rows in memory order (b,q,m), 1 = (b,m,q)
@@ -282,6 +283,89 @@ bool launch_bwd_v2(const msda_dims *d, const Geometry &g, const void *value, con
     return false;
 }
 
+// ---- v5: lean kernels (2-D grid, 32-bit offsets, all-taps-valid fast path) ---------------------------
+std::atomic<int> g_hoist{0};  // v5 forward: issue all tap loads of a row before consuming any
+
+template <typename T, int DD, int LL, int PP, int W>
+void fwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                   const void *attn, void *out, cudaStream_t st)
+{
+    const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
+    const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
+    const bool hoist = g_hoist.load() != 0;
+    if (hoist)
+        msda::msda_fwd_v5<T, DD, LL, PP, W, true><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
+            (int)d->num_heads, rpi);
+    else
+        msda::msda_fwd_v5<T, DD, LL, PP, W, false><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
+            (int)d->num_heads, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v5<%s,D%d,L%d,P%d,w%d%s>", tname<T>(), DD, LL, PP, W,
+             hoist ? ",hoisted" : "");
+}
+
+template <typename T>
+struct BwdChunk {
+    using type = msda::Chunk<T>;
+};
+template <>
+struct BwdChunk<__nv_bfloat16> {
+    using type = msda::ChunkBf16x4;
+};
+
+template <typename T, int DD, int LL, int PP, int W>
+void bwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                   const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
+    const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
+    msda::msda_bwd_v5<T, typename BwdChunk<T>::type, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
+        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, gv_acc,
+        (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v5<%s,D%d,L%d,P%d,w%d>", tname<T>(), DD, LL, PP, W);
+}
+
+template <typename T>
+bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                   const void *attn, void *out, cudaStream_t st)
+{
+    constexpr int E = msda::Chunk<T>::E;
+    if (d->batch > 65535) return false;  // gridDim.y
+    const bool w8 = g_warps.load() >= 8;
+#define X(DD, LL, PP)                                                                                  \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                            \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                   \
+            w8 ? fwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, out, st)            \
+               : fwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, out, st);           \
+            return true;                                                                               \
+        }                                                                                              \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+    return false;
+}
+
+template <typename T>
+bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                   const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    constexpr int E = BwdChunk<T>::type::E;
+    if (d->batch > 65535) return false;
+    const bool w8 = g_warps.load() >= 8;
+#define X(DD, LL, PP)                                                                                             \
+    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                       \
+        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                              \
+            w8 ? bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st) \
+               : bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st);\
+            return true;                                                                                          \
+        }                                                                                                         \
+    }
+    MSDA_FOR_EACH_SPEC(X)
+#undef X
+    return false;
+}
+
 // ---- v3: persistent CTAs with shared-memory staging ------------------------------------------------
 struct DeviceInfo {
     int sms = 0;
@@ -432,6 +516,7 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "head_major")) knob = &g_head_major;
     if (key && !strcmp(key, "warps")) knob = &g_warps;
     if (key && !strcmp(key, "v3_threads")) knob = &g_v3_threads;
+    if (key && !strcmp(key, "hoist")) knob = &g_hoist;
     if (key && !strcmp(key, "v3_min_rows")) knob = &g_v3_min_rows;
     if (!knob) return -1;
     return knob->exchange(value);
@@ -470,6 +555,11 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
             if (rc > 0) return rc;
             done = rc == 0;
         }
+        if (!done && g_variant.load() == 5)
+            done = dtype == MSDA_F32 ? launch_fwd_v5<float>(dims, value, spatial_shapes, level_start_index,
+                                                           sampling_loc, attn_weight, output, st)
+                                     : launch_fwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
+                                                                   sampling_loc, attn_weight, output, st);
         if (!done && g_variant.load() == 4 && dims->channels == 32 && dims->num_levels == 4 && dims->num_point == 4 &&
             dtype == MSDA_F32) {
             const int w = g_warps.load();
@@ -575,6 +665,14 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
             if (rc > 0) return rc;
             done = rc == 0;
         }
+        if (!done && g_variant.load() == 5)
+            done = dtype == MSDA_F32
+                       ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                              attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                              grad_attn_weight, st)
+                       : launch_bwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                      attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                      grad_attn_weight, st);
         if (!done && g_variant.load() != 1) {
             done = dtype == MSDA_F32
                        ? launch_bwd_v2<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,

@@ -1,0 +1,275 @@
+// msda_kernels_v5.cuh -- "lean" specialised kernels (sm_100a): same algorithm as msda_kernels_v2.cuh
+// (warp per row, resolve once, lane group per tap), re-cut after reading the v2 SASS, which spent
+//   ~40 instructions/row on two runtime integer divisions (row -> image, head),
+//   ~6 instructions per tap on 64-bit address arithmetic,
+//   30 CS2R + predicate logic per row zero-filling registers for taps that are almost never out of range,
+//   17 branches per row around the predicated `red`s of the backward.
+// Changes:
+//   * 2-D grid: blockIdx.y is the image, blockIdx.x walks the image's (query, head) rows -> no division
+//     (head = row & (M-1) when M is a power of two);
+//   * 32-bit intra-image element offsets, one IMAD.WIDE per tap address;
+//   * a warp-uniform fast path when all taps of all the row's points are inside the map (the common
+//     case): unconditional loads / reds, no zero-fill, no predicates; the general path keeps the
+//     per-tap predicates, with predicated `red` issued from inline PTX so no branch is needed.
+#pragma once
+
+#include "msda_kernels_v2.cuh"
+
+namespace msda {
+
+__device__ __forceinline__ void red_add_f32x4_if(float *p, float a, float b, float c, float d, int pred)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %5, 0;\n\t@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p),
+        "f"(a), "f"(b), "f"(c), "f"(d), "r"(pred)
+        : "memory");
+}
+
+template <int E, bool ALL>
+__device__ __forceinline__ void red_chunk(float *p, const float (&g)[E], float s, int pred)
+{
+#pragma unroll
+    for (int i = 0; i < E; i += 4) {
+        if (ALL)
+            red_add_f32x4(p + i, s * g[i], s * g[i + 1], s * g[i + 2], s * g[i + 3]);
+        else
+            red_add_f32x4_if(p + i, s * g[i], s * g[i + 1], s * g[i + 2], s * g[i + 3], pred);
+    }
+}
+
+template <typename T, typename CH, bool ALL>
+__device__ __forceinline__ void load_taps(const T *vimg, int o0, int o1, int o2, int o3, int pm, float (&v0)[CH::E],
+                                          float (&v1)[CH::E], float (&v2)[CH::E], float (&v3)[CH::E])
+{
+    if (ALL) {
+        CH::load(vimg + o0, v0);
+        CH::load(vimg + o1, v1);
+        CH::load(vimg + o2, v2);
+        CH::load(vimg + o3, v3);
+    } else {
+#pragma unroll
+        for (int e = 0; e < CH::E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+        if (pm & 1) CH::load(vimg + o0, v0);
+        if (pm & 2) CH::load(vimg + o1, v1);
+        if (pm & 4) CH::load(vimg + o2, v2);
+        if (pm & 8) CH::load(vimg + o3, v3);
+    }
+}
+
+template <typename T, int D, int L, int P, bool ALL>
+__device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg, int MD, const int (&sW)[L], int g,
+                                             float (&acc)[Chunk<T>::E])
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int G = 32 / (D / E);
+    constexpr int PPG = L * P / G;
+#pragma unroll
+    for (int it = 0; it < PPG; ++it) {
+        const int pt = it * G + g;
+        const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+        const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+        const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+        const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+        const int o0 = (pm >> 4) * MD, o1 = o0 + MD;
+        const int o2 = o0 + sW[pt / P] * MD, o3 = o2 + MD;
+        float v0[E], v1[E], v2[E], v3[E];
+        load_taps<T, Chunk<T>, ALL>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
+        const float ah = a - a * lh, al = a * lh, hw = 1.f - lw;
+        const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+    }
+}
+
+// Two-phase variant: phase 1 issues the tap loads of ALL the row's points (16 x LDG.E.128 per lane at D=32, L=P=4)
+// before phase 2 consumes any of them, trading registers (the taps of a whole row are live at once) for
+// memory-level parallelism: the v2 forward is latency-bound (row latency ~5400 cycles at ~36 warps/SM).
+template <typename T, int D, int L, int P, bool ALL>
+__device__ __forceinline__ void fwd_row_body_hoisted(const Resolved &mine, const T *vimg, int MD, const int (&sW)[L],
+                                                     int g, float (&acc)[Chunk<T>::E])
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int G = 32 / (D / E);
+    constexpr int PPG = L * P / G;
+    float v[PPG][4][E];
+    float w[PPG][4];
+#pragma unroll
+    for (int it = 0; it < PPG; ++it) {
+        const int pt = it * G + g;
+        const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+        const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+        const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+        const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+        const int o0 = (pm >> 4) * MD, o1 = o0 + MD;
+        const int o2 = o0 + sW[pt / P] * MD, o3 = o2 + MD;
+        static_assert(ALL, "the hoisted body is the all-taps-valid fast path");
+        Chunk<T>::load_ordered(vimg + o0, v[it][0]);
+        Chunk<T>::load_ordered(vimg + o1, v[it][1]);
+        Chunk<T>::load_ordered(vimg + o2, v[it][2]);
+        Chunk<T>::load_ordered(vimg + o3, v[it][3]);
+        const float ah = a - a * lh, al = a * lh, hw = 1.f - lw;
+        w[it][0] = ah * hw, w[it][1] = ah * lw, w[it][2] = al * hw, w[it][3] = al * lw;
+    }
+    // scheduling fence: every loaded register passes through an (empty) volatile asm, so no consumer can be
+    // scheduled above it and all loads are issued before the first FMA waits on the scoreboard
+#pragma unroll
+    for (int it = 0; it < PPG; ++it)
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int e = 0; e < E; e += 4)
+                asm volatile("" : "+f"(v[it][t][e]), "+f"(v[it][t][e + 1]), "+f"(v[it][t][e + 2]), "+f"(v[it][t][e + 3]));
+#pragma unroll
+    for (int it = 0; it < PPG; ++it) {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            acc[e] = fmaf(w[it][0], v[it][0][e],
+                          fmaf(w[it][1], v[it][1][e], fmaf(w[it][2], v[it][2][e], fmaf(w[it][3], v[it][3][e], acc[e]))));
+    }
+}
+
+template <typename T, int D, int L, int P, int WARPS, bool HOIST = false>
+__global__ void __launch_bounds__(WARPS * 32)
+msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+            const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int M,
+            unsigned rows_per_image)
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+
+    __shared__ int sH[L], sW[L], sStart[L];
+    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPT, sub = lane % LPT;
+    const unsigned r = blockIdx.x * WARPS + (threadIdx.x >> 5);  // (q*M + m) inside image blockIdx.y
+    if (r >= rows_per_image) return;
+    const unsigned m = ((M & (M - 1)) == 0) ? (r & (unsigned)(M - 1)) : (r % (unsigned)M);
+    const int MD = M * D;
+    const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
+    const T *vimg = value + ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
+
+    const int rp = lane % LP;
+    const int rl = rp / P;
+    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + row * LP + rp);
+    const Resolved mine = resolve_point(xy.x, xy.y, sH[rl], sW[rl], sStart[rl], attn + row * LP + rp);
+
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    if (__all_sync(0xffffffffu, (mine.pm & 15) == 15)) {
+        if (HOIST)
+            fwd_row_body_hoisted<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+        else
+            fwd_row_body<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+    } else {
+        fwd_row_body<T, D, L, P, false>(mine, vimg, MD, sW, g, acc);
+    }
+
+#pragma unroll
+    for (int off = LPT; off < 32; off <<= 1) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+    }
+    if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+}
+
+template <typename T, typename CH, int D, int L, int P, bool ALL>
+__device__ __forceinline__ void bwd_row_body(const Resolved &mine, const T *vimg, float *gimg, int MD,
+                                             const int (&sW)[L], int g, const float (&go)[CH::E],
+                                             float (&part)[3 * (L * P / (32 / (D / CH::E)))])
+{
+    constexpr int E = CH::E;
+    constexpr int G = 32 / (D / E);
+    constexpr int PPG = L * P / G;
+#pragma unroll
+    for (int it = 0; it < PPG; ++it) {
+        const int pt = it * G + g;
+        const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
+        const float a = __shfl_sync(0xffffffffu, mine.a, pt);
+        const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
+        const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
+        const int o0 = (pm >> 4) * MD, o1 = o0 + MD;
+        const int o2 = o0 + sW[pt / P] * MD, o3 = o2 + MD;
+        float v0[E], v1[E], v2[E], v3[E];
+        load_taps<T, CH, ALL>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
+        const float hh = 1.f - lh, hw = 1.f - lw;
+        const float ah = a * hh, al = a * lh;
+        red_chunk<E, ALL>(gimg + o0, go, ah * hw, pm & 1);
+        red_chunk<E, ALL>(gimg + o1, go, ah * lw, pm & 2);
+        red_chunk<E, ALL>(gimg + o2, go, al * hw, pm & 4);
+        red_chunk<E, ALL>(gimg + o3, go, al * lw, pm & 8);
+        float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            d0 = fmaf(go[e], v0[e], d0);
+            d1 = fmaf(go[e], v1[e], d1);
+            d2 = fmaf(go[e], v2[e], d2);
+            d3 = fmaf(go[e], v3[e], d3);
+        }
+        const float top = d1 - d0, bot = d3 - d2;  // d/dx of the two tap rows
+        part[3 * it + 0] = hh * fmaf(lw, top, d0) + lh * fmaf(lw, bot, d2);
+        part[3 * it + 1] = a * fmaf(lh, bot - top, top);
+        part[3 * it + 2] = a * fmaf(lw, (d3 - d1) - (d2 - d0), d2 - d0);
+    }
+}
+
+template <typename T, typename CH, int D, int L, int P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))  // <= 64 registers: 32 resident warps per SM
+msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+            const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
+            float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M,
+            unsigned rows_per_image)
+{
+    constexpr int E = CH::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    constexpr int PPG = LP / G;
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+    static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
+
+    __shared__ int sH[L], sW[L], sStart[L];
+    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPT, sub = lane % LPT;
+    const unsigned r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= rows_per_image) return;
+    const unsigned m = ((M & (M - 1)) == 0) ? (r & (unsigned)(M - 1)) : (r % (unsigned)M);
+    const int MD = M * D;
+    const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
+    const int64_t img = ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
+    const T *vimg = value + img;
+    float *gimg = gv_acc + img;
+
+    const int rp = lane % LP;
+    const int rl = rp / P;
+    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + row * LP + rp);
+    const Resolved mine = resolve_point(xy.x, xy.y, sH[rl], sW[rl], sStart[rl], attn + row * LP + rp);
+
+    float go[E];
+    CH::load(grad_out + row * D + sub * E, go);
+
+    float part[3 * PPG];
+    if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
+        bwd_row_body<T, CH, D, L, P, true>(mine, vimg, gimg, MD, sW, g, go, part);
+    else
+        bwd_row_body<T, CH, D, L, P, false>(mine, vimg, gimg, MD, sW, g, go, part);
+
+    group_reduce3<PPG, LPT>(part, sub);
+    constexpr int SPAN = LPT / PPG;
+    if (sub % SPAN == 0) {
+        const int pt = (sub / SPAN) * G + g;
+        const int l = pt / P;
+        reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] =
+            make_float2((float)sW[l] * part[1], (float)sH[l] * part[2]);
+        grad_attn[row * LP + pt] = part[0];
+    }
+}
+
+}  // namespace msda

@@ -88,8 +88,10 @@ const char *msda_last_kernel(void);
 int64_t msda_launch_count(int reset);
 
 /* Tuning / A-B testing knob (process-wide).  Keys:
- *   "variant"     1 first-generation kernels | 2 resolve-once kernels (default) | 3 persistent shared-memory-staged
- *                 kernels | 4 persistent forward with software prefetch | 0 choose 3 or 2 by problem size
+ *   "variant"     1 first-generation kernels | 2 resolve-once kernels | 3 persistent shared-memory-staged kernels |
+ *                 4 persistent forward with software prefetch | 5 lean resolve-once kernels (default) |
+ *                 0 choose 3 or 2 by problem size
+ *   "hoist"       0 | 1   (variant 5 forward: issue all tap loads of a row before the first FMA)
  *   "head_major"  0 | 1   (variant 2: row order)        "warps"  4 | 8 | 16  (variant 2/4: warps per CTA, D=32 L=P=4)
  *   "v3_threads"  512 | 1024                             "v3_min_rows"  threshold of the size heuristic
  * Returns the previous value, or -1 for an unknown key.  Results do not depend on the knobs beyond fp rounding. */

@@ -44,7 +44,7 @@ def main():
     print(f"{'variant:hm:warps':18s} {'fwd ms':>8s} {'frac':>6s} {'bwd ms':>8s} {'frac':>6s} {'Mq/s f+b':>9s}  kernels / max err vs first config")
     for spec in args.configs.split(","):
         variant, hm, warps = (int(x) for x in spec.split(":"))
-        _lib.set_tuning("variant", variant), _lib.set_tuning("head_major", hm)
+        _lib.set_tuning("variant", variant), _lib.set_tuning("head_major", hm), _lib.set_tuning("hoist", hm)
         _lib.set_tuning("v3_threads" if variant == 3 else "warps", warps)
         s = sets[0]
         out = _lib.forward(s["value"], shapes, lsi, s["loc"], s["attn"])

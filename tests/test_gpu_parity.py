@@ -161,6 +161,8 @@ KERNEL_GENERATIONS = [  # (msda_set_tuning settings, expected kernel-name prefix
     ({"variant": 3, "v3_threads": 512}, "v3"),
     ({"variant": 3, "v3_threads": 1024}, "v3"),
     ({"variant": 4, "warps": 8}, "v2"),
+    ({"variant": 5, "warps": 4, "hoist": 0}, "v5"),
+    ({"variant": 5, "warps": 8, "hoist": 1}, "v5"),
 ]
 
 
