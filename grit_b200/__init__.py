@@ -8,10 +8,11 @@ host-side mirror of the reference interface (ops/).
 """
 import sys
 
-from .ops.functions import MSDeformAttnFunction, ms_deform_attn_core_pytorch  # noqa: F401
+from .ops.functions import MSDeformAttnFunction, ms_deform_attn_core_pytorch, set_deterministic  # noqa: F401
 from .ops.modules import MSDeformAttn  # noqa: F401
 
-__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "install_as_reference_ops"]
+__all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "install_as_reference_ops",
+           "set_deterministic"]
 
 
 def install_as_reference_ops(alias_models_ops: bool = True):

@@ -164,12 +164,12 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
     ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags)
-    if code == MSDA_BF16:
+    if ws_bytes:  # bf16 and/or deterministic: accumulation happens in the workspace, a fold kernel writes grad_value
         grad_value = torch.empty_like(value)
         flags |= FLAG_ZERO_GRAD_VALUE  # the fold kernel then overwrites instead of accumulating
     else:
         grad_value = torch.zeros_like(value)
-    workspace = torch.empty(ws_bytes // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+    workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.msda_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),

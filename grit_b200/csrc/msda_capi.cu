@@ -14,6 +14,7 @@
 #include "msda_kernels_v5.cuh"
 
 #include <atomic>
+#include <type_traits>
 
 namespace {
 
@@ -316,14 +317,23 @@ struct BwdChunk<__nv_bfloat16> {
 
 template <typename T, int DD, int LL, int PP, int W>
 void bwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                   const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+                   const void *attn, const void *gout, void *gv_acc, const float *det_scale, void *gloc, void *gattn,
+                   cudaStream_t st)
 {
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
-    msda::msda_bwd_v5<T, typename BwdChunk<T>::type, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
-        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, gv_acc,
-        (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi);
-    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v5<%s,D%d,L%d,P%d,w%d>", tname<T>(), DD, LL, PP, W);
+    using CH = typename BwdChunk<T>::type;
+    if (det_scale)
+        msda::msda_bwd_v5<T, CH, msda::AccFix64, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout,
+            (unsigned long long *)gv_acc, det_scale, (float *)gloc, (float *)gattn, (int)d->spatial_size,
+            (int)d->num_heads, rpi);
+    else
+        msda::msda_bwd_v5<T, CH, msda::AccF32, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, (float *)gv_acc,
+            nullptr, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v5<%s,D%d,L%d,P%d,w%d%s>", tname<T>(), DD, LL, PP, W,
+             det_scale ? ",deterministic" : "");
 }
 
 template <typename T>
@@ -348,7 +358,8 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
 
 template <typename T>
 bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                   const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+                   const void *attn, const void *gout, void *gv_acc, const float *det_scale, void *gloc, void *gattn,
+                   cudaStream_t st)
 {
     constexpr int E = BwdChunk<T>::type::E;
     if (d->batch > 65535) return false;
@@ -356,8 +367,10 @@ bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
 #define X(DD, LL, PP)                                                                                             \
     if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                       \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                              \
-            w8 ? bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st) \
-               : bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st);\
+            w8 ? bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,   \
+                                                 gattn, st)                                                       \
+               : bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,   \
+                                                 gattn, st);                                                      \
             return true;                                                                                          \
         }                                                                                                         \
     }
@@ -489,12 +502,22 @@ void launch_fwd_generic(const msda_dims *d, const Geometry &g, const void *value
 template <typename T, typename C>
 void launch_bwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
                         const int64_t *lsi, const void *loc, const void *attn, const void *gout, void *gv_acc,
-                        void *gloc, void *gattn, cudaStream_t st, const char *name)
+                        const float *det_scale, void *gloc, void *gattn, cudaStream_t st, const char *name)
 {
     const size_t smem = 3 * sizeof(int) * (size_t)d->num_levels;
-    msda::msda_bwd_generic<T, C, kWarps><<<g.grid, kWarps * 32, smem, st>>>(
-        (const T *)value, shapes, lsi, (const C *)loc, (const C *)attn, (const T *)gout, (C *)gv_acc, (C *)gloc,
-        (C *)gattn, d->spatial_size, (int)d->num_heads, (int)d->channels, (int)d->num_levels, d->num_query,
+    if constexpr (std::is_same<C, float>::value) {
+        if (det_scale) {
+            msda::msda_bwd_generic<T, C, unsigned long long, kWarps><<<g.grid, kWarps * 32, smem, st>>>(
+                (const T *)value, shapes, lsi, (const C *)loc, (const C *)attn, (const T *)gout,
+                (unsigned long long *)gv_acc, det_scale, (C *)gloc, (C *)gattn, d->spatial_size, (int)d->num_heads,
+                (int)d->channels, (int)d->num_levels, d->num_query, (int)d->num_point, g.rows);
+            snprintf(tl_kernel, sizeof(tl_kernel), "bwd_generic<%s,deterministic>", name);
+            return;
+        }
+    }
+    msda::msda_bwd_generic<T, C, C, kWarps><<<g.grid, kWarps * 32, smem, st>>>(
+        (const T *)value, shapes, lsi, (const C *)loc, (const C *)attn, (const T *)gout, (C *)gv_acc, nullptr,
+        (C *)gloc, (C *)gattn, d->spatial_size, (int)d->num_heads, (int)d->channels, (int)d->num_levels, d->num_query,
         (int)d->num_point, g.rows);
     snprintf(tl_kernel, sizeof(tl_kernel), "bwd_generic<%s>", name);
 }
@@ -604,10 +627,11 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
 
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags)
 {
-    (void)flags;
     if (!dims) return 0;
-    if (dtype == MSDA_BF16)  // fp32 accumulation image of grad_value
-        return (size_t)(dims->batch * dims->spatial_size * dims->num_heads * dims->channels) * sizeof(float);
+    const size_t n_value = (size_t)(dims->batch * dims->spatial_size * dims->num_heads * dims->channels);
+    if ((flags & MSDA_FLAG_DETERMINISTIC) && dtype != MSDA_F64)
+        return n_value * sizeof(long long) + 16;  // int64 fixed-point accumulators + {max|attn|, max|g|, 2^k, 2^-k}
+    if (dtype == MSDA_BF16) return n_value * sizeof(float);  // fp32 accumulation image of grad_value
     return 0;
 }
 
@@ -618,21 +642,30 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 {
     tl_error[0] = 0;
     if (int rc = check_dims(dims, dtype)) return rc;
-    if (flags & MSDA_FLAG_DETERMINISTIC)
-        return fail(MSDA_ERR_UNSUPPORTED, "deterministic backward is not built into this version");
+    const bool det = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
+    if (det && dtype == MSDA_F64)
+        return fail(MSDA_ERR_UNSUPPORTED, "deterministic backward supports f32 and bf16 (int64 fixed point cannot "
+                                          "carry fp64 precision)");
     Geometry g;
     if (int rc = geometry(dims, &g)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+    const bool zero_first = (flags & MSDA_FLAG_ZERO_GRAD_VALUE) != 0;
+    const bool via_workspace = det || dtype == MSDA_BF16;  // grad_value is produced by a fold kernel
 
     if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
-    if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && dtype != MSDA_BF16)
+    if (zero_first && n_value > 0 && (!via_workspace || g.rows == 0))
         if (int rc = check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * dtype_size(dtype), st),
                                 "memset grad_value"))
             return rc;
-    if (g.rows == 0) {
-        if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && dtype == MSDA_BF16)
-            return check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * 2, st), "memset grad_value");
+    if (g.rows == 0 || n_value == 0) {
+        if (g.rows > 0) {  // no value pixels at all: every sample is out of range, all gradients are zero
+            const size_t el = dtype == MSDA_F64 ? 8 : 4;
+            const size_t pts = (size_t)g.rows * dims->num_levels * dims->num_point;
+            if (!grad_sampling_loc || !grad_attn_weight) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+            cudaMemsetAsync(grad_sampling_loc, 0, pts * 2 * el, st);
+            return check_cuda(cudaMemsetAsync(grad_attn_weight, 0, pts * el, st), "memset gradients");
+        }
         return MSDA_OK;
     }
     if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
@@ -640,21 +673,42 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
 
     void *gv_acc = grad_value;
-    if (dtype == MSDA_BF16) {
+    const float *det_scale = nullptr;
+    unsigned *tail = nullptr;
+    if (via_workspace) {
         const size_t need = msda_backward_workspace_bytes(dims, dtype, flags);
         if (!workspace || workspace_bytes < need)
-            return fail(MSDA_ERR_WORKSPACE, "bf16 backward needs a %zu-byte workspace, got %zu", need,
-                        workspace_bytes);
+            return fail(MSDA_ERR_WORKSPACE, "this backward needs a %zu-byte workspace, got %zu", need, workspace_bytes);
         if (!aligned16(workspace)) return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
         if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, need, st), "memset workspace")) return rc;
         gv_acc = workspace;
+        if (det) {
+            tail = reinterpret_cast<unsigned *>(static_cast<char *>(workspace) + (size_t)n_value * sizeof(long long));
+            det_scale = reinterpret_cast<const float *>(tail) + 2;
+            const int64_t n_attn = g.rows * dims->num_levels * dims->num_point;
+            const int64_t n_gout = g.rows * dims->channels;
+            const int blocks = 148 * 8;
+            if (dtype == MSDA_F32)
+                msda::msda_det_absmax<float><<<blocks, 256, 0, st>>>((const float *)attn_weight, n_attn,
+                                                                     (const float *)grad_output, n_gout, tail);
+            else
+                msda::msda_det_absmax<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+                    (const float *)attn_weight, n_attn, (const __nv_bfloat16 *)grad_output, n_gout, tail);
+            // one element of grad_value receives at most one tap of each (query, level, point) of its image and head
+            const double worst = (double)dims->num_query * (double)dims->num_levels * (double)dims->num_point;
+            msda::msda_det_scale<<<1, 1, 0, st>>>(tail, worst);
+            tl_launches += 2;
+            if (int rc = check_cuda(cudaPeekAtLastError(), "deterministic pre-pass launch")) return rc;
+        }
     }
 
     bool done = false;
+    const int variant = g_variant.load();
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) && aligned16(gv_acc) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
         (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0) {
-        if (v3_wanted(dims) && dims->batch < (1 << 30) && dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
+        if (!det && v3_wanted(dims) && dims->batch < (1 << 30) &&
+            dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
             const int rc =
                 dtype == MSDA_F32
                     ? launch_bwd_v3<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
@@ -665,15 +719,15 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
             if (rc > 0) return rc;
             done = rc == 0;
         }
-        if (!done && g_variant.load() == 5)
+        if (!done && (variant == 5 || det))  // the deterministic accumulator exists in the v5 and generic kernels
             done = dtype == MSDA_F32
                        ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                              attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                              attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
                                               grad_attn_weight, st)
                        : launch_bwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                                      attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                      attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
                                                       grad_attn_weight, st);
-        if (!done && g_variant.load() != 1) {
+        if (!done && !det && variant != 1) {
             done = dtype == MSDA_F32
                        ? launch_bwd_v2<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
                                               attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
@@ -682,7 +736,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
                                                       attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
                                                       grad_attn_weight, st);
         }
-        if (!done)
+        if (!done && !det)
             done = dtype == MSDA_F32
                        ? launch_bwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
                                                attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
@@ -694,30 +748,42 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     if (!done) {
         if (dtype == MSDA_F32)
             launch_bwd_generic<float, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                             attn_weight, grad_output, gv_acc, grad_sampling_loc, grad_attn_weight,
-                                             st, "f32");
+                                             attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
+                                             grad_attn_weight, st, "f32");
         else if (dtype == MSDA_F64)
             launch_bwd_generic<double, double>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                               attn_weight, grad_output, gv_acc, grad_sampling_loc, grad_attn_weight,
-                                               st, "f64");
+                                               attn_weight, grad_output, gv_acc, nullptr, grad_sampling_loc,
+                                               grad_attn_weight, st, "f64");
         else
             launch_bwd_generic<__nv_bfloat16, float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                                     attn_weight, grad_output, gv_acc, grad_sampling_loc,
+                                                     attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
                                                      grad_attn_weight, st, "bf16");
     }
     ++tl_launches;
     if (int rc = check_cuda(cudaPeekAtLastError(), "msda_backward launch")) return rc;
 
-    if (dtype == MSDA_BF16) {
+    if (via_workspace) {
         const int threads = 256;
-        int64_t blocks = (n_value / 8 + threads - 1) / threads;
-        if (blocks < 1) blocks = 1;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
-            (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value,
-            (flags & MSDA_FLAG_ZERO_GRAD_VALUE) ? 0 : 1);
+        const int accumulate = zero_first ? 0 : 1;
+        if (det) {
+            const int blocks = 148 * 16;
+            if (dtype == MSDA_F32)
+                msda::msda_det_fold<float><<<blocks, threads, 0, st>>>((const long long *)workspace,
+                                                                      (const float *)tail, (float *)grad_value,
+                                                                      n_value, accumulate);
+            else
+                msda::msda_det_fold<__nv_bfloat16><<<blocks, threads, 0, st>>>(
+                    (const long long *)workspace, (const float *)tail, (__nv_bfloat16 *)grad_value, n_value,
+                    accumulate);
+        } else {
+            int64_t blocks = (n_value / 8 + threads - 1) / threads;
+            if (blocks < 1) blocks = 1;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
+                (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value, accumulate);
+        }
         ++tl_launches;
-        if (int rc = check_cuda(cudaPeekAtLastError(), "msda_fold_workspace_bf16 launch")) return rc;
+        if (int rc = check_cuda(cudaPeekAtLastError(), "fold launch")) return rc;
     }
     return MSDA_OK;
 }

@@ -423,13 +423,26 @@ msda_fwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
 }
 
 // A = accumulation element of gv_acc: double for fp64, float otherwise (bf16 goes through the workspace).
-template <typename T, typename C, int WARPS>
+template <typename C>
+__device__ __forceinline__ void acc_add(C *p, C v, float)
+{
+    atomicAdd(p, v);
+}
+// deterministic mode: power-of-two scaled int64 fixed point (see AccFix64 in msda_kernels_v5.cuh)
+__device__ __forceinline__ void acc_add(unsigned long long *p, float v, float scale)
+{
+    const long long q = __float2ll_rn(v * scale);
+    if (q != 0) atomicAdd(p, (unsigned long long)q);
+}
+
+template <typename T, typename C, typename A, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                  const C *__restrict__ loc, const C *__restrict__ attn, const T *__restrict__ grad_out,
-                 C *__restrict__ gv_acc, C *__restrict__ grad_loc, C *__restrict__ grad_attn, int64_t S, int M, int D,
-                 int L, int64_t Lq, int P, int64_t rows)
+                 A *__restrict__ gv_acc, const float *__restrict__ det_scale, C *__restrict__ grad_loc,
+                 C *__restrict__ grad_attn, int64_t S, int M, int D, int L, int64_t Lq, int P, int64_t rows)
 {
+    const float fx_scale = det_scale ? __ldg(det_scale) : 1.f;
     extern __shared__ int s_meta[];
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         s_meta[i] = (int)shapes[2 * i];
@@ -464,10 +477,10 @@ msda_bwd_generic(const T *__restrict__ value, const int64_t *__restrict__ shapes
                 const C v2 = t.bl ? to_c<C, T>(value[o1 + c]) : (C)0;
                 const C v3 = t.br ? to_c<C, T>(value[o1 + MD + c]) : (C)0;
                 const C ga = gch * a;
-                if (t.tl) atomicAdd(gv_acc + o0 + c, w0 * ga);
-                if (t.tr) atomicAdd(gv_acc + o0 + MD + c, w1 * ga);
-                if (t.bl) atomicAdd(gv_acc + o1 + c, w2 * ga);
-                if (t.br) atomicAdd(gv_acc + o1 + MD + c, w3 * ga);
+                if (t.tl) acc_add(gv_acc + o0 + c, w0 * ga, fx_scale);
+                if (t.tr) acc_add(gv_acc + o0 + MD + c, w1 * ga, fx_scale);
+                if (t.bl) acc_add(gv_acc + o1 + c, w2 * ga, fx_scale);
+                if (t.br) acc_add(gv_acc + o1 + MD + c, w3 * ga, fx_scale);
                 s_a += gch * (w0 * v0 + w1 * v1 + w2 * v2 + w3 * v3);
                 s_x += gch * (t.hh * (v1 - v0) + t.lh * (v3 - v2));
                 s_y += gch * (t.hw * (v2 - v0) + t.lw * (v3 - v1));

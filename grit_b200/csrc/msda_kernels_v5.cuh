@@ -37,6 +37,37 @@ __device__ __forceinline__ void red_chunk(float *p, const float (&g)[E], float s
     }
 }
 
+// ---- grad_value accumulation policies ------------------------------------------------------------------------------
+// AccF32  : fp32 vector reductions (REDG.E.ADD.F32x4).  Fast; summation order, hence the last bits, vary run to run.
+// AccFix64: deterministic.  Every contribution is scaled by a power of two chosen on the device from max|attn| *
+//           max|grad_out| and the worst-case number of addends, rounded to int64 and added with integer atomics;
+//           integer addition is associative, so the result is bit-reproducible (and is the correctly rounded exact
+//           sum up to 2^-k).  Costs 8-byte scalar reds instead of 16-byte vector ones.
+struct AccF32 {
+    using elem = float;
+    template <int E, bool ALL>
+    __device__ __forceinline__ void add(float *p, const float (&g)[E], float s, int pred) const
+    {
+        red_chunk<E, ALL>(p, g, s, pred);
+    }
+};
+
+struct AccFix64 {
+    using elem = unsigned long long;
+    float scale;  // 2^k
+    template <int E, bool ALL>
+    __device__ __forceinline__ void add(unsigned long long *p, const float (&g)[E], float s, int pred) const
+    {
+        if (ALL || pred) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const long long q = __float2ll_rn(s * g[e] * scale);
+                if (q != 0) atomicAdd(p + e, (unsigned long long)q);
+            }
+        }
+    }
+};
+
 template <typename T, typename CH, bool ALL>
 __device__ __forceinline__ void load_taps(const T *vimg, int o0, int o1, int o2, int o3, int pm, float (&v0)[CH::E],
                                           float (&v1)[CH::E], float (&v2)[CH::E], float (&v3)[CH::E])
@@ -178,8 +209,9 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
 }
 
-template <typename T, typename CH, int D, int L, int P, bool ALL>
-__device__ __forceinline__ void bwd_row_body(const Resolved &mine, const T *vimg, float *gimg, int MD,
+template <typename T, typename CH, typename ACC, int D, int L, int P, bool ALL>
+__device__ __forceinline__ void bwd_row_body(const ACC &accp, const Resolved &mine, const T *vimg,
+                                             typename ACC::elem *gimg, int MD,
                                              const int (&sW)[L], int g, const float (&go)[CH::E],
                                              float (&part)[3 * (L * P / (32 / (D / CH::E)))])
 {
@@ -199,10 +231,10 @@ __device__ __forceinline__ void bwd_row_body(const Resolved &mine, const T *vimg
         load_taps<T, CH, ALL>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
         const float hh = 1.f - lh, hw = 1.f - lw;
         const float ah = a * hh, al = a * lh;
-        red_chunk<E, ALL>(gimg + o0, go, ah * hw, pm & 1);
-        red_chunk<E, ALL>(gimg + o1, go, ah * lw, pm & 2);
-        red_chunk<E, ALL>(gimg + o2, go, al * hw, pm & 4);
-        red_chunk<E, ALL>(gimg + o3, go, al * lw, pm & 8);
+        accp.template add<E, ALL>(gimg + o0, go, ah * hw, pm & 1);
+        accp.template add<E, ALL>(gimg + o1, go, ah * lw, pm & 2);
+        accp.template add<E, ALL>(gimg + o2, go, al * hw, pm & 4);
+        accp.template add<E, ALL>(gimg + o3, go, al * lw, pm & 8);
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -218,12 +250,12 @@ __device__ __forceinline__ void bwd_row_body(const Resolved &mine, const T *vimg
     }
 }
 
-template <typename T, typename CH, int D, int L, int P, int WARPS>
+template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))  // <= 64 registers: 32 resident warps per SM
 msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
-            float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M,
-            unsigned rows_per_image)
+            typename ACC::elem *__restrict__ gv_acc, const float *__restrict__ det_scale,
+            float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, unsigned rows_per_image)
 {
     constexpr int E = CH::E;
     constexpr int LPT = D / E;
@@ -245,7 +277,9 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
     const int64_t img = ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
     const T *vimg = value + img;
-    float *gimg = gv_acc + img;
+    typename ACC::elem *gimg = gv_acc + img;
+    ACC accp;
+    if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
 
     const int rp = lane % LP;
     const int rl = rp / P;
@@ -257,9 +291,9 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
 
     float part[3 * PPG];
     if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
-        bwd_row_body<T, CH, D, L, P, true>(mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, true>(accp, mine, vimg, gimg, MD, sW, g, go, part);
     else
-        bwd_row_body<T, CH, D, L, P, false>(mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part);
 
     group_reduce3<PPG, LPT>(part, sub);
     constexpr int SPAN = LPT / PPG;
@@ -269,6 +303,57 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
         reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] =
             make_float2((float)sW[l] * part[1], (float)sH[l] * part[2]);
         grad_attn[row * LP + pt] = part[0];
+    }
+}
+
+// ---- deterministic mode helpers ---------------------------------------------------------------------------------------
+// workspace tail: [0] = max|attn| bits, [1] = max|grad_out| bits (uint, monotone for non-negative floats),
+//                 [2] = scale 2^k (float), [3] = 2^-k (float)
+template <typename T>
+__global__ void msda_det_absmax(const float *__restrict__ attn, int64_t n_attn, const T *__restrict__ gout,
+                                int64_t n_gout, unsigned *__restrict__ tail)
+{
+    float ma = 0.f, mg = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_attn; i += stride) ma = fmaxf(ma, fabsf(attn[i]));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_gout; i += stride)
+        mg = fmaxf(mg, fabsf(to_c<float, T>(gout[i])));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+        mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(tail + 0, __float_as_uint(ma));
+        atomicMax(tail + 1, __float_as_uint(mg));
+    }
+}
+
+// One thread: k = 61 - ceil(log2(worst-case addends)) - exponent(max|attn| * max|grad_out|), so that the int64 sums
+// cannot overflow whatever the sampling pattern is.
+__global__ void msda_det_scale(unsigned *tail, double worst_addends)
+{
+    const float ma = __uint_as_float(tail[0]), mg = __uint_as_float(tail[1]);
+    int e_prod = 0, e_n = 0;
+    frexp((double)ma * (double)mg, &e_prod);  // product < 2^e_prod
+    frexp(worst_addends, &e_n);                // addends < 2^e_n
+    int k = 61 - e_n - e_prod;
+    if (!(ma > 0.f) || !(mg > 0.f)) k = 0;     // all-zero (or NaN) inputs: any scale works
+    k = max(-100, min(100, k));
+    reinterpret_cast<float *>(tail)[2] = ldexpf(1.f, k);
+    reinterpret_cast<float *>(tail)[3] = ldexpf(1.f, -k);
+}
+
+template <typename T>
+__global__ void msda_det_fold(const long long *__restrict__ acc, const float *__restrict__ tail, T *__restrict__ gv,
+                              int64_t n, int accumulate)
+{
+    const double inv = (double)tail[3];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float r = (float)((double)acc[i] * inv);
+        if (accumulate) r += to_c<float, T>(gv[i]);
+        gv[i] = from_c<T, float>(r);
     }
 }
 

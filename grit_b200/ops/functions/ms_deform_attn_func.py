@@ -14,11 +14,31 @@ kernels cover the whole batch in one launch, so the value is only validated to b
 bf16: ``value`` may be bf16 (output and grad_value are then bf16, accumulation is fp32).  ``sampling_locations`` /
 ``attention_weights`` are used in fp32; bf16 ones are up-cast here (bf16 cannot resolve pixel coordinates).
 """
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from ... import _lib
+
+_deterministic = os.environ.get("GRIT_B200_DETERMINISTIC", "0") not in ("", "0", "false", "False")
+
+
+def set_deterministic(enabled: bool) -> bool:
+    """Select the bit-reproducible backward (MSDA_FLAG_DETERMINISTIC: grad_value accumulated as power-of-two scaled
+    int64 fixed point with integer atomics; fp32 / bf16 values).  Also switched on by
+    ``torch.use_deterministic_algorithms(True)`` or ``GRIT_B200_DETERMINISTIC=1``.  Returns the previous setting.
+    The reference backward (float atomicAdd, ms_deform_im2col_cuda.cuh:87-159) has no such mode."""
+    global _deterministic
+    prev, _deterministic = _deterministic, bool(enabled)
+    return prev
+
+
+def _backward_flags(dtype) -> int:
+    if dtype != torch.float64 and (_deterministic or torch.are_deterministic_algorithms_enabled()):
+        return _lib.FLAG_DETERMINISTIC
+    return 0
 
 
 class MSDeformAttnFunction(Function):
@@ -45,7 +65,7 @@ class MSDeformAttnFunction(Function):
         value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
         grad_value, grad_sampling_loc, grad_attn_weight = _lib.backward(
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
-            grad_output.contiguous())
+            grad_output.contiguous(), _backward_flags(value.dtype))
         if grad_sampling_loc.dtype != ctx.loc_dtype:
             grad_sampling_loc = grad_sampling_loc.to(ctx.loc_dtype)
         if grad_attn_weight.dtype != ctx.attn_dtype:
