@@ -65,6 +65,16 @@ def load():
         lib.msda_backward.restype = ctypes.c_int
         lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint,
                                       vp, ctypes.c_size_t, vp]
+        lib.msda_fused_supported.restype = ctypes.c_int
+        lib.msda_fused_supported.argtypes = [dimsp, ctypes.c_int, ctypes.c_int]
+        lib.msda_mask_rows.restype = ctypes.c_int
+        lib.msda_mask_rows.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int64, vp]
+        lib.msda_fused_forward.restype = ctypes.c_int
+        lib.msda_fused_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, ctypes.c_int, vp, dimsp, ctypes.c_int,
+                                           ctypes.c_uint, vp]
+        lib.msda_fused_backward.restype = ctypes.c_int
+        lib.msda_fused_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, dimsp,
+                                            ctypes.c_int, ctypes.c_uint, vp, ctypes.c_size_t, vp]
         lib.msda_host_session_create.restype = ctypes.c_int
         lib.msda_host_session_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), dimsp, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int]
@@ -180,6 +190,86 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     if rc:
         _raise(lib, rc, "msda_backward")
     return grad_value, grad_loc, grad_attn
+
+
+def fused_dims(value, sampling_offsets, reference_points):
+    n, s, m, d = value.shape
+    _, lq, _, l, p, _ = sampling_offsets.shape
+    return MsdaDims(n, s, m, d, l, lq, p)
+
+
+def fused_supported(value, sampling_offsets, reference_points) -> bool:
+    """True when the fused kernels (include/msda.h: msda_fused_*) cover this problem."""
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    if sampling_offsets.dtype != torch.float32 or reference_points.dtype != torch.float32:
+        return False
+    dims = fused_dims(value, sampling_offsets, reference_points)
+    return bool(load().msda_fused_supported(ctypes.byref(dims), _DTYPE_CODE[value.dtype],
+                                            int(reference_points.shape[-1])))
+
+
+def mask_rows_(data, mask):
+    """In place: data[mask] = 0 for data (..., R) contiguous and mask (...) bool -- value.masked_fill(mask[..., None], 0)."""
+    lib = load()
+    row_bytes = data.shape[-1] * data.element_size() if mask.dim() == data.dim() - 1 else \
+        data[(0,) * mask.dim()].numel() * data.element_size()
+    if not (data.is_contiguous() and mask.is_contiguous() and mask.dtype == torch.bool):
+        raise RuntimeError("mask_rows_ expects contiguous data and a contiguous bool mask")
+    with torch.cuda.device(data.device):
+        rc = lib.msda_mask_rows(_ptr(data), _ptr(mask), mask.numel(), row_bytes,
+                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_mask_rows")
+    return data
+
+
+def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
+    lib = load()
+    for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+                    ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
+                    ("level_start_index", level_start_index)):
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+    dims = fused_dims(value, sampling_offsets, reference_points)
+    out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
+                      device=value.device)
+    with torch.cuda.device(value.device):
+        rc = lib.msda_fused_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
+                                    _ptr(attn_logits), _ptr(reference_points), int(reference_points.shape[-1]),
+                                    _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], 0,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_fused_forward")
+    return out
+
+
+def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                   grad_output, flags: int = 0):
+    lib = load()
+    dims = fused_dims(value, sampling_offsets, reference_points)
+    code = _DTYPE_CODE[value.dtype]
+    grad_offs = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attn_logits)
+    ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags)
+    if ws_bytes:
+        grad_value = torch.empty_like(value)
+        flags |= FLAG_ZERO_GRAD_VALUE
+    else:
+        grad_value = torch.zeros_like(value)
+    workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        rc = lib.msda_fused_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+                                     _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
+                                     int(reference_points.shape[-1]), _ptr(grad_output), _ptr(grad_value),
+                                     _ptr(grad_offs), _ptr(grad_logits), ctypes.byref(dims), code, flags,
+                                     _ptr(workspace) if workspace is not None else None, ws_bytes,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_fused_backward")
+    return grad_value, grad_offs, grad_logits
 
 
 class HostSession:

@@ -11,7 +11,7 @@
 #include <cstring>
 
 #include "msda_kernels_v3.cuh"
-#include "msda_kernels_v5.cuh"
+#include "msda_kernels_fused.cuh"
 
 #include <atomic>
 #include <type_traits>
@@ -635,6 +635,118 @@ size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned 
     return 0;
 }
 
+}  // extern "C" (helpers below need internal linkage)
+
+namespace {
+
+// grad_value accumulation target: grad_value itself (f32/f64), or the caller's workspace (bf16: fp32 image;
+// deterministic: int64 fixed point + scale tail) that a fold kernel turns into grad_value afterwards.
+struct AccPlan {
+    void *gv_acc = nullptr;
+    const float *det_scale = nullptr;
+    unsigned *tail = nullptr;
+    bool via_workspace = false;
+    bool det = false;
+};
+
+// attn == nullptr means "attention weights are a softmax output, bounded by 1" (fused path)
+int acc_begin(const msda_dims *dims, const Geometry &g, int dtype, unsigned flags, void *grad_value, void *workspace,
+              size_t workspace_bytes, const void *attn, const void *grad_output, cudaStream_t st, AccPlan *plan)
+{
+    const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+    plan->det = (flags & MSDA_FLAG_DETERMINISTIC) != 0;
+    plan->via_workspace = plan->det || dtype == MSDA_BF16;
+    plan->gv_acc = grad_value;
+    if (!plan->via_workspace) return MSDA_OK;
+    const size_t need = msda_backward_workspace_bytes(dims, dtype, flags);
+    if (!workspace || workspace_bytes < need)
+        return fail(MSDA_ERR_WORKSPACE, "this backward needs a %zu-byte workspace, got %zu", need, workspace_bytes);
+    if (!aligned16(workspace)) return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, need, st), "memset workspace")) return rc;
+    plan->gv_acc = workspace;
+    if (plan->det) {
+        plan->tail = reinterpret_cast<unsigned *>(static_cast<char *>(workspace) + (size_t)n_value * sizeof(long long));
+        plan->det_scale = reinterpret_cast<const float *>(plan->tail) + 2;
+        const int64_t n_attn = attn ? g.rows * dims->num_levels * dims->num_point : 0;
+        const int64_t n_gout = g.rows * dims->channels;
+        const int blocks = 148 * 8;
+        if (dtype == MSDA_F32)
+            msda::msda_det_absmax<float><<<blocks, 256, 0, st>>>((const float *)attn, n_attn,
+                                                                 (const float *)grad_output, n_gout, plan->tail);
+        else
+            msda::msda_det_absmax<__nv_bfloat16><<<blocks, 256, 0, st>>>(
+                (const float *)attn, n_attn, (const __nv_bfloat16 *)grad_output, n_gout, plan->tail);
+        // one element of grad_value receives at most one tap of each (query, level, point) of its image and head
+        const double worst = (double)dims->num_query * (double)dims->num_levels * (double)dims->num_point;
+        msda::msda_det_scale<<<1, 1, 0, st>>>(plan->tail, worst, attn ? 0.f : 1.f);
+        tl_launches += 2;
+        if (int rc = check_cuda(cudaPeekAtLastError(), "deterministic pre-pass launch")) return rc;
+    }
+    return MSDA_OK;
+}
+
+int acc_end(const msda_dims *dims, int dtype, unsigned flags, void *grad_value, void *workspace, const AccPlan &plan,
+            cudaStream_t st)
+{
+    if (!plan.via_workspace) return MSDA_OK;
+    const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+    const int threads = 256;
+    const int accumulate = (flags & MSDA_FLAG_ZERO_GRAD_VALUE) ? 0 : 1;
+    if (plan.det) {
+        const int blocks = 148 * 16;
+        if (dtype == MSDA_F32)
+            msda::msda_det_fold<float><<<blocks, threads, 0, st>>>((const long long *)workspace,
+                                                                  (const float *)plan.tail, (float *)grad_value,
+                                                                  n_value, accumulate);
+        else
+            msda::msda_det_fold<__nv_bfloat16><<<blocks, threads, 0, st>>>(
+                (const long long *)workspace, (const float *)plan.tail, (__nv_bfloat16 *)grad_value, n_value,
+                accumulate);
+    } else {
+        int64_t blocks = (n_value / 8 + threads - 1) / threads;
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
+            (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value, accumulate);
+    }
+    ++tl_launches;
+    return check_cuda(cudaPeekAtLastError(), "fold launch");
+}
+
+// zero-fills shared by the plain and the fused backward; returns 1 when there is nothing left to launch
+int backward_prologue(const msda_dims *dims, const Geometry &g, int dtype, unsigned flags, void *grad_value,
+                      void *grad_pts2, void *grad_pts1, cudaStream_t st, int *rc_out)
+{
+    const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+    const bool via_workspace = (flags & MSDA_FLAG_DETERMINISTIC) || dtype == MSDA_BF16;
+    *rc_out = MSDA_OK;
+    if (n_value > 0 && !grad_value) {
+        *rc_out = fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
+        return 1;
+    }
+    if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && (!via_workspace || g.rows == 0))
+        if ((*rc_out = check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * dtype_size(dtype), st),
+                                  "memset grad_value")))
+            return 1;
+    if (g.rows == 0) return 1;
+    if (n_value == 0) {  // no value pixels at all: every sample is out of range, all gradients are zero
+        const size_t el = dtype == MSDA_F64 ? 8 : 4;
+        const size_t pts = (size_t)g.rows * dims->num_levels * dims->num_point;
+        if (!grad_pts2 || !grad_pts1) {
+            *rc_out = fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+            return 1;
+        }
+        cudaMemsetAsync(grad_pts2, 0, pts * 2 * el, st);
+        *rc_out = check_cuda(cudaMemsetAsync(grad_pts1, 0, pts * el, st), "memset gradients");
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                   const void *sampling_loc, const void *attn_weight, const void *grad_output, void *grad_value,
                   void *grad_sampling_loc, void *grad_attn_weight, const msda_dims *dims, int dtype, unsigned flags,
@@ -649,58 +761,18 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     Geometry g;
     if (int rc = geometry(dims, &g)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
-    const bool zero_first = (flags & MSDA_FLAG_ZERO_GRAD_VALUE) != 0;
-    const bool via_workspace = det || dtype == MSDA_BF16;  // grad_value is produced by a fold kernel
-
-    if (n_value > 0 && !grad_value) return fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
-    if (zero_first && n_value > 0 && (!via_workspace || g.rows == 0))
-        if (int rc = check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * dtype_size(dtype), st),
-                                "memset grad_value"))
-            return rc;
-    if (g.rows == 0 || n_value == 0) {
-        if (g.rows > 0) {  // no value pixels at all: every sample is out of range, all gradients are zero
-            const size_t el = dtype == MSDA_F64 ? 8 : 4;
-            const size_t pts = (size_t)g.rows * dims->num_levels * dims->num_point;
-            if (!grad_sampling_loc || !grad_attn_weight) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
-            cudaMemsetAsync(grad_sampling_loc, 0, pts * 2 * el, st);
-            return check_cuda(cudaMemsetAsync(grad_attn_weight, 0, pts * el, st), "memset gradients");
-        }
-        return MSDA_OK;
-    }
+    int rc0 = MSDA_OK;
+    if (backward_prologue(dims, g, dtype, flags, grad_value, grad_sampling_loc, grad_attn_weight, st, &rc0)) return rc0;
     if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
         !grad_sampling_loc || !grad_attn_weight)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
 
-    void *gv_acc = grad_value;
-    const float *det_scale = nullptr;
-    unsigned *tail = nullptr;
-    if (via_workspace) {
-        const size_t need = msda_backward_workspace_bytes(dims, dtype, flags);
-        if (!workspace || workspace_bytes < need)
-            return fail(MSDA_ERR_WORKSPACE, "this backward needs a %zu-byte workspace, got %zu", need, workspace_bytes);
-        if (!aligned16(workspace)) return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
-        if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, need, st), "memset workspace")) return rc;
-        gv_acc = workspace;
-        if (det) {
-            tail = reinterpret_cast<unsigned *>(static_cast<char *>(workspace) + (size_t)n_value * sizeof(long long));
-            det_scale = reinterpret_cast<const float *>(tail) + 2;
-            const int64_t n_attn = g.rows * dims->num_levels * dims->num_point;
-            const int64_t n_gout = g.rows * dims->channels;
-            const int blocks = 148 * 8;
-            if (dtype == MSDA_F32)
-                msda::msda_det_absmax<float><<<blocks, 256, 0, st>>>((const float *)attn_weight, n_attn,
-                                                                     (const float *)grad_output, n_gout, tail);
-            else
-                msda::msda_det_absmax<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-                    (const float *)attn_weight, n_attn, (const __nv_bfloat16 *)grad_output, n_gout, tail);
-            // one element of grad_value receives at most one tap of each (query, level, point) of its image and head
-            const double worst = (double)dims->num_query * (double)dims->num_levels * (double)dims->num_point;
-            msda::msda_det_scale<<<1, 1, 0, st>>>(tail, worst);
-            tl_launches += 2;
-            if (int rc = check_cuda(cudaPeekAtLastError(), "deterministic pre-pass launch")) return rc;
-        }
-    }
+    AccPlan plan;
+    if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, attn_weight, grad_output, st,
+                           &plan))
+        return rc;
+    void *gv_acc = plan.gv_acc;
+    const float *det_scale = plan.det_scale;
 
     bool done = false;
     const int variant = g_variant.load();
@@ -761,31 +833,174 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     }
     ++tl_launches;
     if (int rc = check_cuda(cudaPeekAtLastError(), "msda_backward launch")) return rc;
+    return acc_end(dims, dtype, flags, grad_value, workspace, plan, st);
+}
 
-    if (via_workspace) {
-        const int threads = 256;
-        const int accumulate = zero_first ? 0 : 1;
-        if (det) {
-            const int blocks = 148 * 16;
-            if (dtype == MSDA_F32)
-                msda::msda_det_fold<float><<<blocks, threads, 0, st>>>((const long long *)workspace,
-                                                                      (const float *)tail, (float *)grad_value,
-                                                                      n_value, accumulate);
-            else
-                msda::msda_det_fold<__nv_bfloat16><<<blocks, threads, 0, st>>>(
-                    (const long long *)workspace, (const float *)tail, (__nv_bfloat16 *)grad_value, n_value,
-                    accumulate);
-        } else {
-            int64_t blocks = (n_value / 8 + threads - 1) / threads;
-            if (blocks < 1) blocks = 1;
-            if (blocks > 148 * 16) blocks = 148 * 16;
-            msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
-                (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value, accumulate);
-        }
-        ++tl_launches;
-        if (int rc = check_cuda(cudaPeekAtLastError(), "fold launch")) return rc;
+// ---- fused module path (softmax + sampling-location arithmetic inside the kernels) --------------------------------
+
+#define MSDA_FOR_EACH_FUSED_SPEC(X) \
+    X(32, 4, 4)                     \
+    X(64, 4, 4)
+
+int msda_fused_supported(const msda_dims *dims, int dtype, int ref_dim)
+{
+    if (!dims || (dtype != MSDA_F32 && dtype != MSDA_BF16) || (ref_dim != 2 && ref_dim != 4)) return 0;
+    if (!vec_eligible(dims, dtype, 0) || dims->batch > 65535) return 0;
+#define X(DD, LL, PP) \
+    if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) return 1;
+    MSDA_FOR_EACH_FUSED_SPEC(X)
+#undef X
+    return 0;
+}
+
+int msda_mask_rows(void *data, const unsigned char *mask, int64_t n_rows, int64_t row_bytes, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (n_rows <= 0 || row_bytes <= 0) return MSDA_OK;
+    if (!data || !mask) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if (row_bytes % 16 != 0 || !aligned16(data) || row_bytes > 0x7fffffff)
+        return fail(MSDA_ERR_UNSUPPORTED, "msda_mask_rows needs 16-byte aligned rows");
+    int64_t blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    msda::msda_mask_rows<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>((float *)data, mask, n_rows,
+                                                                                         (int)row_bytes);
+    ++tl_launches;
+    return check_cuda(cudaPeekAtLastError(), "msda_mask_rows launch");
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T, int DD, int LL, int PP, int RD>
+void fused_fwd_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi,
+                      const void *offs, const void *logits, const void *ref, void *out, cudaStream_t st)
+{
+    constexpr int W = 4;
+    const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
+    const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
+    msda::msda_fwd_fused<T, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
+        (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref, (T *)out,
+        (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_fused<%s,D%d,L%d,P%d,ref%d>", tname<T>(), DD, LL, PP, RD);
+}
+
+template <typename T, int DD, int LL, int PP, int RD>
+void fused_bwd_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi,
+                      const void *offs, const void *logits, const void *ref, const void *gout, void *gv_acc,
+                      const float *det_scale, void *goffs, void *glogits, cudaStream_t st)
+{
+    constexpr int W = 4;
+    const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
+    const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
+    using CH = typename BwdChunk<T>::type;
+    if (det_scale)
+        msda::msda_bwd_fused<T, CH, msda::AccFix64, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
+            (const T *)gout, (unsigned long long *)gv_acc, det_scale, (float *)goffs, (float *)glogits,
+            (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
+    else
+        msda::msda_bwd_fused<T, CH, msda::AccF32, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
+            (const T *)gout, (float *)gv_acc, nullptr, (float *)goffs, (float *)glogits, (int)d->spatial_size,
+            (int)d->num_heads, (int)d->num_query, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_fused<%s,D%d,L%d,P%d,ref%d%s>", tname<T>(), DD, LL, PP, RD,
+             det_scale ? ",deterministic" : "");
+}
+
+}  // namespace
+
+extern "C" {
+
+int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                       int ref_dim, void *output, const msda_dims *dims, int dtype, unsigned flags, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    (void)flags;
+    if (int rc = check_dims(dims, dtype)) return rc;
+    if (!msda_fused_supported(dims, dtype, ref_dim))
+        return fail(MSDA_ERR_UNSUPPORTED, "no fused specialisation for D=%lld L=%lld P=%lld dtype=%s ref_dim=%d",
+                    (long long)dims->channels, (long long)dims->num_levels, (long long)dims->num_point,
+                    dtype_name(dtype), ref_dim);
+    Geometry g;
+    if (int rc = geometry(dims, &g)) return rc;
+    if (g.rows == 0) return MSDA_OK;
+    if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
+        !output)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if (!aligned16(value) || !aligned16(output) || !aligned16(reference_points) ||
+        (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned value/output/reference_points");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+#define X(DD, LL, PP)                                                                                             \
+    if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) {                         \
+        if (dtype == MSDA_F32)                                                                                    \
+            ref_dim == 2 ? fused_fwd_launch<float, DD, LL, PP, 2>(dims, value, spatial_shapes, level_start_index, \
+                                                                  sampling_offsets, attn_logits, reference_points, \
+                                                                  output, st)                                     \
+                         : fused_fwd_launch<float, DD, LL, PP, 4>(dims, value, spatial_shapes, level_start_index, \
+                                                                  sampling_offsets, attn_logits, reference_points, \
+                                                                  output, st);                                    \
+        else                                                                                                      \
+            ref_dim == 2 ? fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 2>(dims, value, spatial_shapes,            \
+                                                                          level_start_index, sampling_offsets,    \
+                                                                          attn_logits, reference_points, output,  \
+                                                                          st)                                     \
+                         : fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 4>(dims, value, spatial_shapes,            \
+                                                                          level_start_index, sampling_offsets,    \
+                                                                          attn_logits, reference_points, output,  \
+                                                                          st);                                    \
     }
-    return MSDA_OK;
+    MSDA_FOR_EACH_FUSED_SPEC(X)
+#undef X
+    ++tl_launches;
+    return check_cuda(cudaPeekAtLastError(), "msda_fused_forward launch");
+}
+
+int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                        int ref_dim, const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits,
+                        const msda_dims *dims, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
+                        void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (int rc = check_dims(dims, dtype)) return rc;
+    if (!msda_fused_supported(dims, dtype, ref_dim))
+        return fail(MSDA_ERR_UNSUPPORTED, "no fused specialisation for this shape/dtype");
+    Geometry g;
+    if (int rc = geometry(dims, &g)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc0 = MSDA_OK;
+    if (backward_prologue(dims, g, dtype, flags, grad_value, grad_offsets, grad_logits, st, &rc0)) return rc0;
+    if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
+        !grad_output || !grad_offsets || !grad_logits)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    AccPlan plan;
+    if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, nullptr, grad_output, st,
+                           &plan))
+        return rc;
+    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(plan.gv_acc) || !aligned16(reference_points) ||
+        (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u) || (reinterpret_cast<uintptr_t>(grad_offsets) & 7u))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned tensors");
+#define ARGS                                                                                                    \
+    dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output, \
+        plan.gv_acc, plan.det_scale, grad_offsets, grad_logits, st
+#define X(DD, LL, PP)                                                                                 \
+    if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) {             \
+        if (dtype == MSDA_F32)                                                                        \
+            ref_dim == 2 ? fused_bwd_launch<float, DD, LL, PP, 2>(ARGS)                               \
+                         : fused_bwd_launch<float, DD, LL, PP, 4>(ARGS);                              \
+        else                                                                                          \
+            ref_dim == 2 ? fused_bwd_launch<__nv_bfloat16, DD, LL, PP, 2>(ARGS)                       \
+                         : fused_bwd_launch<__nv_bfloat16, DD, LL, PP, 4>(ARGS);                      \
+    }
+    MSDA_FOR_EACH_FUSED_SPEC(X)
+#undef X
+#undef ARGS
+    ++tl_launches;
+    if (int rc = check_cuda(cudaPeekAtLastError(), "msda_fused_backward launch")) return rc;
+    return acc_end(dims, dtype, flags, grad_value, workspace, plan, st);
 }
 
 // ---- host-buffer session ---------------------------------------------------------------------------

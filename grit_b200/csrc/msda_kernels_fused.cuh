@@ -1,0 +1,194 @@
+// msda_kernels_fused.cuh -- the pre-op arithmetic of MSDeformAttn.forward fused into the gather.
+//
+// The reference module (models/ops/modules/ms_deform_attn.py:96-111) runs, between its Linears and the core op,
+// a chain of elementwise PyTorch kernels: masked_fill on value, softmax over the L*P logits, offsets / normaliser,
+// + reference points -- each a full read+write pass over tensors as large as `value` itself, and their autograd
+// counterparts in backward.  Here the kernels take the Linears' raw outputs:
+//     offsets (N, Lq, M, L, P, 2), logits (N, Lq, M, L*P), reference_points (N, Lq, L, 2|4)
+// and the resolver lane of each sample point does softmax (two shuffle reductions over the row's L*P lanes) and
+//     loc = ref.xy + off / (W_l, H_l)                    2-d reference points   (reference :105-108)
+//     loc = ref.xy + off / P * ref.wh * 0.5              4-d reference boxes    (reference :109-111)
+// in registers; sampling_locations / attention_weights are never materialised.  The backward emits grad_offsets and
+// grad_logits directly (softmax backward = one extra warp reduction per row); grad of the reference points, when
+// needed, is a cheap reduction of grad_offsets done by the caller.  The padding mask is applied by msda_mask_rows
+// (zero the masked pixels' rows in place: traffic proportional to the padded fraction, not to the tensor).
+#pragma once
+
+#include "msda_kernels_v5.cuh"
+
+namespace msda {
+
+template <int LP>
+__device__ __forceinline__ float segment_max(float v)
+{
+#pragma unroll
+    for (int off = LP / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+template <int LP>
+__device__ __forceinline__ float segment_sum(float v)
+{
+#pragma unroll
+    for (int off = LP / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// Softmax weight and sampling location of point `rp` of row `row`, from the Linears' raw outputs.
+template <int L, int P, int RD>
+__device__ __forceinline__ void fused_point(const float *__restrict__ offs, const float *__restrict__ logits,
+                                            const float *__restrict__ ref, int64_t row, int64_t bq, int rp, int rl,
+                                            int H, int W, float &a_soft, float &x, float &y)
+{
+    constexpr int LP = L * P;
+    const float lg = __ldg(logits + row * LP + rp);
+    const float mx = segment_max<LP>(lg);
+    const float ex = exp2f((lg - mx) * 1.4426950408889634f);
+    a_soft = ex / segment_sum<LP>(ex);
+    const float2 of = __ldg(reinterpret_cast<const float2 *>(offs) + row * LP + rp);
+    if (RD == 2) {
+        const float2 rf = __ldg(reinterpret_cast<const float2 *>(ref) + bq * L + rl);
+        x = rf.x + of.x / (float)W;
+        y = rf.y + of.y / (float)H;
+    } else {
+        const float4 rf = __ldg(reinterpret_cast<const float4 *>(ref) + bq * L + rl);
+        x = rf.x + of.x / (float)P * rf.z * 0.5f;
+        y = rf.y + of.y / (float)P * rf.w * 0.5f;
+    }
+}
+
+template <typename T, int D, int L, int P, int WARPS, int RD>
+__global__ void __launch_bounds__(WARPS * 32)
+msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+               const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
+               T *__restrict__ out, int S, int M, int Lq, unsigned rows_per_image)
+{
+    constexpr int E = Chunk<T>::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+
+    __shared__ int sH[L], sW[L], sStart[L];
+    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPT, sub = lane % LPT;
+    const unsigned r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= rows_per_image) return;
+    const bool pow2 = (M & (M - 1)) == 0;
+    const unsigned m = pow2 ? (r & (unsigned)(M - 1)) : (r % (unsigned)M);
+    const unsigned q = pow2 ? (r >> (31 - __clz(M))) : (r / (unsigned)M);
+    const int MD = M * D;
+    const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
+    const int64_t bq = (int64_t)blockIdx.y * Lq + q;
+    const T *vimg = value + ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
+
+    const int rp = lane % LP;
+    const int rl = rp / P;
+    float a_soft, x, y;
+    fused_point<L, P, RD>(offs, logits, ref, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
+
+    float acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = 0.f;
+    if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
+        fwd_row_body<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+    else
+        fwd_row_body<T, D, L, P, false>(mine, vimg, MD, sW, g, acc);
+#pragma unroll
+    for (int off = LPT; off < 32; off <<= 1) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+    }
+    if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+}
+
+template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS, int RD>
+__global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))
+msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
+               const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
+               const T *__restrict__ grad_out, typename ACC::elem *__restrict__ gv_acc,
+               const float *__restrict__ det_scale, float *__restrict__ grad_offs, float *__restrict__ grad_logits,
+               int S, int M, int Lq, unsigned rows_per_image)
+{
+    constexpr int E = CH::E;
+    constexpr int LPT = D / E;
+    constexpr int G = 32 / LPT;
+    constexpr int LP = L * P;
+    constexpr int PPG = LP / G;
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+    static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
+
+    __shared__ int sH[L], sW[L], sStart[L];
+    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPT, sub = lane % LPT;
+    const unsigned r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= rows_per_image) return;
+    const bool pow2 = (M & (M - 1)) == 0;
+    const unsigned m = pow2 ? (r & (unsigned)(M - 1)) : (r % (unsigned)M);
+    const unsigned q = pow2 ? (r >> (31 - __clz(M))) : (r / (unsigned)M);
+    const int MD = M * D;
+    const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
+    const int64_t bq = (int64_t)blockIdx.y * Lq + q;
+    const int64_t img = ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
+    const T *vimg = value + img;
+    typename ACC::elem *gimg = gv_acc + img;
+    ACC accp;
+    if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
+
+    const int rp = lane % LP;
+    const int rl = rp / P;
+    float a_soft, x, y;
+    fused_point<L, P, RD>(offs, logits, ref, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
+
+    float go[E];
+    CH::load(grad_out + row * D + sub * E, go);
+
+    float part[3 * PPG];
+    if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
+        bwd_row_body<T, CH, ACC, D, L, P, true>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+    else
+        bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+    group_reduce3<PPG, LPT>(part, sub);
+
+    // after the reduction lane (g, sub) with sub % SPAN == 0 holds point pt: part[0] = d out/d attn,
+    // part[1], part[2] = a * d val / d(w_im, h_im)
+    constexpr int SPAN = LPT / PPG;
+    const bool holder = (sub % SPAN) == 0;
+    const int pt = (sub / SPAN) * G + g;
+    const float a_pt = __shfl_sync(0xffffffffu, a_soft, pt);  // the TRUE softmax weight, also for skipped points
+    float dot = holder ? a_pt * part[0] : 0.f;                // softmax backward: sum_j a_j * dL/da_j over the row
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if (holder) {
+        const int l = pt / P;
+        grad_logits[row * LP + pt] = a_pt * (part[0] - dot);
+        float gx = part[1], gy = part[2];  // 2-d: d loc/d off = 1/(W,H) cancels the (W,H) of d(w_im,h_im)/d loc
+        if (RD == 4) {
+            const float4 rf = __ldg(reinterpret_cast<const float4 *>(ref) + bq * L + l);
+            gx = (float)sW[l] * gx * (rf.z * 0.5f / (float)P);
+            gy = (float)sH[l] * gy * (rf.w * 0.5f / (float)P);
+        }
+        reinterpret_cast<float2 *>(grad_offs)[row * LP + pt] = make_float2(gx, gy);
+    }
+}
+
+// Zero the channel rows of masked pixels in place: rows (n_rows, row_elems) of T, mask (n_rows,) of bytes.
+template <typename T>
+__global__ void msda_mask_rows(T *__restrict__ data, const unsigned char *__restrict__ mask, int64_t n_rows,
+                               int row_bytes)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t rowi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rowi < n_rows; rowi += warps) {
+        if (!mask[rowi]) continue;
+        uint4 *p = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(data) + rowi * row_bytes);
+        for (int i = lane; i < row_bytes / 16; i += 32) p[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+}  // namespace msda

@@ -331,9 +331,11 @@ __global__ void msda_det_absmax(const float *__restrict__ attn, int64_t n_attn, 
 
 // One thread: k = 61 - ceil(log2(worst-case addends)) - exponent(max|attn| * max|grad_out|), so that the int64 sums
 // cannot overflow whatever the sampling pattern is.
-__global__ void msda_det_scale(unsigned *tail, double worst_addends)
+__global__ void msda_det_scale(unsigned *tail, double worst_addends, float attn_bound)
 {
-    const float ma = __uint_as_float(tail[0]), mg = __uint_as_float(tail[1]);
+    // attn_bound > 0: the caller knows max|attn| a priori (softmax output <= 1 in the fused path)
+    const float ma = attn_bound > 0.f ? attn_bound : __uint_as_float(tail[0]);
+    const float mg = __uint_as_float(tail[1]);
     int e_prod = 0, e_n = 0;
     frexp((double)ma * (double)mg, &e_prod);  // product < 2^e_prod
     frexp(worst_addends, &e_n);                // addends < 2^e_n

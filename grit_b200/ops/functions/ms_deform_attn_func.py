@@ -73,6 +73,56 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
 
 
+class MSDeformAttnFusedFunction(Function):
+    """The core op with the module's pre-op arithmetic inside the kernels: takes the RAW outputs of
+    the ``sampling_offsets`` / ``attention_weights`` Linears plus the reference points; softmax, ``offsets/normaliser +
+    reference`` and the padding-mask fill (reference modules/ms_deform_attn.py:96-111) never touch HBM as separate
+    passes.  ``value`` is the value_proj output (N, S, M, D); when ``padding_mask`` is given its masked rows are zeroed
+    IN PLACE (and the same rows of grad_value in backward).  Not part of the reference API: ``MSDeformAttn`` uses it
+    when ``module.fused`` is on and ``_lib.fused_supported`` says yes."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_offsets, attn_logits,
+                reference_points, padding_mask):
+        if padding_mask is not None:
+            # raw in-place write (no autograd version bump): `value` is the value_proj output, whose producer
+            # (addmm) does not need its own output in backward; the matching rows of grad_value are zeroed below
+            _lib.mask_rows_(value, padding_mask)
+        ctx.has_mask = padding_mask is not None
+        sampling_offsets = sampling_offsets.contiguous()
+        attn_logits = attn_logits.contiguous()
+        reference_points = reference_points.contiguous()
+        output = _lib.fused_forward(value, value_spatial_shapes, value_level_start_index, sampling_offsets,
+                                    attn_logits, reference_points)
+        saved = [value, value_spatial_shapes, value_level_start_index, sampling_offsets, attn_logits, reference_points]
+        if padding_mask is not None:
+            saved.append(padding_mask)
+        ctx.save_for_backward(*saved)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, lsi, offsets, logits, ref = ctx.saved_tensors[:6]
+        grad_value, grad_offs, grad_logits = _lib.fused_backward(value, shapes, lsi, offsets, logits, ref,
+                                                                 grad_output.contiguous(), _backward_flags(value.dtype))
+        if ctx.has_mask:
+            _lib.mask_rows_(grad_value, ctx.saved_tensors[6])
+        grad_ref = None
+        if ctx.needs_input_grad[5]:
+            n_points = offsets.shape[4]
+            if ref.shape[-1] == 2:  # loc = ref + off / (W, H)  =>  d loc/d ref = 1, grad_loc = grad_off * (W, H)
+                normalizer = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(grad_offs.dtype)
+                grad_ref = (grad_offs * normalizer[None, None, None, :, None, :]).sum(dim=(2, 4))
+            else:  # loc = ref.xy + off / P * ref.wh * 0.5
+                scale = ref[:, :, None, :, None, 2:] * (0.5 / n_points)
+                grad_loc = grad_offs / scale
+                grad_xy = grad_loc.sum(dim=(2, 4))
+                grad_wh = (grad_loc * offsets * (0.5 / n_points)).sum(dim=(2, 4))
+                grad_ref = torch.cat([grad_xy, grad_wh], -1)
+        return grad_value, None, None, grad_offs, grad_logits, grad_ref, None
+
+
 def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
     """Debug/test helper with the reference's name and signature (reference :41-61): the same function written in
     plain differentiable PyTorch (explicit four-tap gathers instead of ``F.grid_sample``).  Works on any device and

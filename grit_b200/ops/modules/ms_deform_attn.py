@@ -17,7 +17,8 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from ..functions import MSDeformAttnFunction
+from ... import _lib
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 
 def _is_power_of_2(n):
@@ -43,6 +44,7 @@ class MSDeformAttn(nn.Module):
 
         self.im2col_step = 64
         self.validate_shapes = True
+        self.fused = True
 
         self.d_model = d_model
         self.n_levels = n_levels
@@ -92,6 +94,20 @@ class MSDeformAttn(nn.Module):
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
         value = self.value_proj(input_flatten)
+        if self.fused and query.is_cuda:
+            # fused path: softmax, offsets/normaliser + reference points and the mask fill happen
+            # inside the gather kernels; falls through to the reference-shaped path when no specialisation exists
+            value4 = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+            offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+            if reference_points.shape[-1] not in (2, 4):
+                raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(
+                    reference_points.shape[-1]))
+            ref32 = reference_points.float()
+            if _lib.fused_supported(value4, offsets.float(), ref32):
+                logits = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+                output = MSDeformAttnFusedFunction.apply(value4, input_spatial_shapes, input_level_start_index,
+                                                         offsets.float(), logits.float(), ref32, input_padding_mask)
+                return self.output_proj(output)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)

@@ -60,7 +60,8 @@ enum {
 /* flags */
 enum {
     MSDA_FLAG_ZERO_GRAD_VALUE = 1u << 0, /* backward: memset grad_value on the stream before accumulating   */
-    MSDA_FLAG_DETERMINISTIC = 1u << 1,   /* backward: bit-reproducible grad_value (order-independent path)  */
+    MSDA_FLAG_DETERMINISTIC = 1u << 1,   /* backward (f32/bf16): bit-reproducible grad_value -- int64 fixed-point   */
+                                         /* accumulation with integer atomics; needs the workspace                  */
     MSDA_FLAG_FORCE_GENERIC = 1u << 2    /* testing: skip the specialised kernels, use the generic ones     */
 };
 
@@ -102,7 +103,8 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
                  const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims,
                  int dtype, unsigned flags, void *cuda_stream);
 
-/* Bytes of device scratch msda_backward needs for this problem (0 for f32/f64 without flags). */
+/* Bytes of device scratch msda_backward needs for this problem: 0 for f32/f64; N*S*M*D*4 for bf16 (fp32 image of
+ * grad_value); N*S*M*D*8 + 16 with MSDA_FLAG_DETERMINISTIC.  The workspace must be 16-byte aligned. */
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags);
 
 /* grad_value += scatter(w*attn*grad_out); grad_sampling_loc, grad_attn_weight = analytic gradients. */
@@ -110,6 +112,32 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
                   const void *sampling_loc, const void *attn_weight, const void *grad_output,
                   void *grad_value, void *grad_sampling_loc, void *grad_attn_weight, const msda_dims *dims,
                   int dtype, unsigned flags, void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/*
+ * Fused module path -- SURVEY.md section 8f-1.  Replaces, in MSDeformAttn.forward
+ * (models/ops/modules/ms_deform_attn.py:96-111), the elementwise chain between the Linears and the core op:
+ * softmax over the L*P logits, offsets / normaliser + reference points, and the padding-mask fill.
+ *   sampling_offsets (N, Lq, M, L, P, 2) fp32  raw output of the sampling_offsets Linear
+ *   attn_logits      (N, Lq, M, L*P)     fp32  raw output of the attention_weights Linear (pre-softmax)
+ *   reference_points (N, Lq, L, ref_dim) fp32  ref_dim 2: (x, y);  ref_dim 4: (cx, cy, w, h)
+ * msda_fused_backward writes grad_offsets / grad_logits (same shapes) and accumulates grad_value exactly like
+ * msda_backward (same flags, same workspace rule: msda_backward_workspace_bytes).  The gradient of the reference
+ * points is a reduction of grad_offsets the caller can do when it is needed.
+ * msda_fused_supported() says whether a specialisation exists; callers fall back to msda_forward/backward otherwise.
+ * msda_mask_rows zeroes, in place, the rows r of a (n_rows, row_bytes) array whose mask byte is non-zero
+ * (value.masked_fill(padding_mask[..., None], 0) and its gradient, reference :96-97).
+ */
+int msda_fused_supported(const msda_dims *dims, int dtype, int ref_dim);
+int msda_mask_rows(void *data, const unsigned char *mask, int64_t n_rows, int64_t row_bytes, void *cuda_stream);
+int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                       int ref_dim, void *output, const msda_dims *dims, int dtype, unsigned flags,
+                       void *cuda_stream);
+int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                        int ref_dim, const void *grad_output, void *grad_value, void *grad_offsets,
+                        void *grad_logits, const msda_dims *dims, int dtype, unsigned flags, void *workspace,
+                        size_t workspace_bytes, void *cuda_stream);
 
 /*
  * Host-buffer path (what a caller without device tensors uses; bench.py's "e2e" leg).

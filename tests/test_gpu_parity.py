@@ -345,6 +345,120 @@ def test_module_matches_reference_module(lib, name, dtype):
         assert max_norm_err(p.grad.cpu().numpy(), g["grad." + k]) < tol, k
 
 
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 64)])
+def test_fused_module_matches_unfused_fp64(lib, ref_dim, dtype, D):
+    """MSDeformAttn with the fused kernels (softmax + location arithmetic + mask inside the gather)
+    against the reference-shaped path of the same module run in fp64 (generic fp64 kernels, themselves pinned to the
+    reference module's golden vectors above).  Includes gradients w.r.t. query, memory, reference points, parameters."""
+    import copy
+
+    from grit_b200 import MSDeformAttn
+    torch.manual_seed(7)
+    N, Lq, M, L, P = 2, 77, 8, 4, 4
+    C = M * D
+    shapes_l = [(14, 18), (7, 9), (4, 5), (2, 3)]
+    S = sum(h * w for h, w in shapes_l)
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.from_numpy(helpers.level_start(shapes_l)).cuda()
+    mod = MSDeformAttn(C, L, M, P).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.3 / C ** 0.5)
+        mod.attention_weights.weight.normal_(0, 1.0 / C ** 0.5)
+        mod.attention_weights.bias.normal_(0, 0.5)
+    ref_mod = copy.deepcopy(mod).double()
+    ref_mod.fused = False
+    mod = mod.to(dtype)
+    assert mod.fused
+    query = torch.randn(N, Lq, C, device="cuda")
+    src = torch.randn(N, S, C, device="cuda")
+    ref_pts = torch.rand(N, Lq, L, 2, device="cuda") * 1.2 - 0.1
+    if ref_dim == 4:
+        ref_pts = torch.cat([ref_pts, torch.rand(N, Lq, L, 2, device="cuda") * 0.6 + 0.05], -1)
+    mask = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    mask[1, ::7] = True
+    gout = torch.randn(N, Lq, C, device="cuda")
+
+    def run(m, dt):
+        q = query.detach().clone().to(dt).requires_grad_(True)
+        s_ = src.detach().clone().to(dt).requires_grad_(True)
+        r = ref_pts.detach().clone().to(dt if dt == torch.float64 else torch.float32).requires_grad_(True)
+        out = m(q, r, s_, shapes, lsi, mask)
+        out.backward(gout.to(dt))
+        grads = dict(query=q.grad, src=s_.grad, ref=r.grad, **{k: p.grad for k, p in m.named_parameters()})
+        return out.detach(), grads
+
+    # the fp64 reference sees the same rounded inputs/weights as the low-precision module
+    for p_ref, p in zip(ref_mod.parameters(), mod.parameters()):
+        p_ref.data.copy_(p.data.double())
+    query, src, gout = query.to(dtype).float(), src.to(dtype).float(), gout.to(dtype).float()
+    out, grads = run(mod, dtype)
+    assert "fused" in lib.last_kernel()
+    out_ref, grads_ref = run(ref_mod, torch.float64)
+    tol = 3e-4 if dtype == torch.float32 else 4e-2  # cuBLAS fp32 Linears + kernel on one side, fp64 on the other
+    assert max_norm_err(out.double().cpu().numpy(), out_ref.cpu().numpy()) < tol
+    for k in grads_ref:
+        assert grads[k] is not None, k
+        assert max_norm_err(grads[k].double().cpu().numpy(), grads_ref[k].cpu().numpy()) < tol, k
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("vdtype,D", [(torch.float32, 32), (torch.bfloat16, 32), (torch.bfloat16, 64)])
+def test_fused_function_vs_oracle(lib, oracle, ref_dim, vdtype, D):
+    """msda_fused_forward/backward through the C ABI vs the CPU oracle fed with softmax / locations computed in fp64
+    (bf16: value and grad_output are bf16, offsets / logits / reference points stay fp32)."""
+    rng = np.random.default_rng(31)
+    N, Lq, M, L, P = 2, 90, 8, 4, 4
+    shapes_l = SMALL_PYR
+    S = sum(h * w for h, w in shapes_l)
+    rnd = lambda a: torch.from_numpy(a).to(vdtype).float().numpy()
+    value = rnd(rng.standard_normal((N, S, M, D)).astype(np.float32))
+    offs = (rng.standard_normal((N, Lq, M, L, P, 2)) * 2.0).astype(np.float32)
+    logits = (rng.standard_normal((N, Lq, M, L * P)) * 2.0).astype(np.float32)
+    ref = (rng.random((N, Lq, L, 2)) * 1.3 - 0.15).astype(np.float32)
+    if ref_dim == 4:
+        ref = np.concatenate([ref, (rng.random((N, Lq, L, 2)) * 0.5 + 0.05).astype(np.float32)], -1)
+    gout = rnd(rng.standard_normal((N, Lq, M * D)).astype(np.float32))
+    shp = np.asarray(shapes_l, dtype=np.float64)
+    o64, r64 = offs.astype(np.float64), ref.astype(np.float64)
+    if ref_dim == 2:
+        loc = r64[:, :, None, :, None, :] + o64 / np.stack([shp[:, 1], shp[:, 0]], -1)[None, None, None, :, None, :]
+    else:
+        loc = r64[:, :, None, :, None, :2] + o64 / P * r64[:, :, None, :, None, 2:] * 0.5
+    attn = oracle.softmax_np(logits.astype(np.float64), -1).reshape(N, Lq, M, L, P)
+    lsi = helpers.level_start(shapes_l)
+    shapes_np = np.asarray(shapes_l, dtype=np.int64)
+    ref_out = oracle.forward(value, shapes_np, lsi, loc, attn)
+    ref_gv, ref_gl, ref_ga = oracle.backward(value, shapes_np, lsi, loc, attn, gout)
+    # chain rule to the raw inputs, in fp64
+    if ref_dim == 2:
+        ref_goff = ref_gl / np.stack([shp[:, 1], shp[:, 0]], -1)[None, None, None, :, None, :]
+    else:
+        ref_goff = ref_gl * (r64[:, :, None, :, None, 2:] * 0.5 / P)
+    ga = ref_ga.reshape(N, Lq, M, L * P)
+    a = attn.reshape(N, Lq, M, L * P)
+    ref_glog = a * (ga - (a * ga).sum(-1, keepdims=True))
+
+    cu = lambda x: torch.from_numpy(x).cuda()
+    v_dev, g_dev = cu(value).to(vdtype), cu(gout).to(vdtype)
+    out = lib.fused_forward(v_dev, cu(shapes_np), cu(lsi), cu(offs), cu(logits), cu(ref))
+    gv, goff, glog = lib.fused_backward(v_dev, cu(shapes_np), cu(lsi), cu(offs), cu(logits), cu(ref), g_dev)
+    ftol, gtol = TOL[vdtype]
+    assert max_norm_err(out.double().cpu().numpy(), ref_out) < ftol
+    assert max_norm_err(gv.double().cpu().numpy(), ref_gv) < gtol
+    assert max_norm_err(glog.cpu().numpy(), ref_glog) < 1e-4
+    keep = ~helpers.tie_mask(loc, shapes_np)
+    assert np.abs((goff.cpu().numpy() - ref_goff)[keep]).max() / np.abs(ref_goff).max() < 1e-4
+
+
+def test_mask_rows(lib):
+    x = torch.randn(3, 50, 8, 32, device="cuda")
+    mask = torch.rand(3, 50, device="cuda") < 0.3
+    want = x.masked_fill(mask[..., None, None], 0.0)
+    got = lib.mask_rows_(x.clone(), mask)
+    assert torch.equal(got, want)
+
+
 def test_module_invalid_reference_points(lib):
     from grit_b200 import MSDeformAttn
     mod = MSDeformAttn(32, 2, 4, 2).cuda()
