@@ -137,6 +137,8 @@ def make_layer_inputs(torch, cfg, device, seed, loc_dist):
     attn = torch.softmax(torch.randn(N, Lq, M, L * P, device=device, generator=gen), -1).view(N, Lq, M, L, P)
     if loc_dist == "uniform":
         loc = torch.rand(N, Lq, M, L, P, 2, device=device, generator=gen) * 1.1 - 0.05
+    elif loc_dist == "concentrated":  # diagnostic: every sample inside a ~2% x 2% window -> taps hit L1
+        loc = 0.5 + torch.rand(N, Lq, M, L, P, 2, device=device, generator=gen) * 0.02
     else:  # detector-like: own pixel centre (encoder) or U[0,1) (decoder) + init ring offsets + N(0, 2 px)
         import math
         if Lq == S:
@@ -206,7 +208,8 @@ def workload_config(args, cfg, world):
             "Lq": cfg["Lq"] or S, "M": cfg["M"], "D": cfg["D"], "L": len(cfg["shapes"]), "P": cfg["P"],
             "level_shapes": cfg["shapes"], "layers_per_step": cfg["layers"], "pass": "forward+backward",
             "loc_dist": {"uniform": "uniform U[-0.05,1.05) (worst-case locality)",
-                         "detector": "detector-like (own pixel + ring offsets + N(0,2px))"}[args.loc_dist],
+                         "detector": "detector-like (own pixel + ring offsets + N(0,2px))",
+                         "concentrated": "diagnostic: all samples in a 2% window (L1-resident taps)"}[args.loc_dist],
             "l2_policy": "inputs larger than L2: every layer reads its own input set (>= 1 GB at the default workload), "
                          "126 MB L2 is cycled between launches",
             "parallelism": f"batch-sharded replicas x{world}"}
@@ -219,7 +222,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="detr_encoder_800x1333")
-    ap.add_argument("--loc-dist", choices=["uniform", "detector"], default="uniform")
+    ap.add_argument("--loc-dist", choices=["uniform", "detector", "concentrated"], default="uniform")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
