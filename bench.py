@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--loc-dist", choices=["uniform", "detector", "concentrated"], default="uniform")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -413,6 +414,56 @@ def main():
         if not torch.equal(out.cpu(), h_out):
             raise RuntimeError("e2e host path and device path disagree")
 
+    # ---- extras (rank 0, N=1): the other location distribution and the reference's own CUDA kernels on this GPU -------
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = {}
+
+        def time_pair(inputs, fwd_fn, bwd_fn, iters=5):
+            res = []
+            for fn in (fwd_fn, bwd_fn):
+                for _ in range(2):
+                    fn(inputs)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(iters):
+                    fn(inputs)
+                b.record()
+                torch.cuda.synchronize()
+                res.append(a.elapsed_time(b) / iters)
+            return res
+
+        other = "detector" if args.loc_dist == "uniform" else "uniform"
+        alt = make_layer_inputs(torch, cfg, device, 77, other)
+
+        def bwd_zero(s):
+            if dt != torch.bfloat16:
+                gv.zero_()
+            bwd(s)
+        f_ms, b_ms = time_pair(alt, fwd, bwd_zero)
+        extras[f"loc_dist_{other}"] = {"fwd_ms": f_ms, "bwd_ms": b_ms, "queries_per_s": N * Lq / ((f_ms + b_ms) * 1e-3)}
+        del alt
+        ref_so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttentionRef.so")
+        if os.path.exists(ref_so) and dt == torch.float32:
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttentionRef", ref_so)
+                refmod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(refmod)
+                s0 = sets[0]
+                f_ms, b_ms = time_pair(
+                    s0, lambda s: refmod.ms_deform_attn_forward(s["value"], shapes, lsi, s["loc"], s["attn"], 64),
+                    lambda s: refmod.ms_deform_attn_backward(s["value"], shapes, lsi, s["loc"], s["attn"], s["gout"],
+                                                             64))
+                mine = (avg_f + avg_b)
+                extras["reference_cuda_kernels_on_this_gpu"] = {
+                    "what": "the reference's own CUDA kernels (models/ops/src/cuda) recompiled for sm_100a "
+                            "(baseline/build_ref_cuda.py), same inputs, incl. their output allocation + zero-fill",
+                    "fwd_ms": f_ms, "bwd_ms": b_ms, "queries_per_s": N * Lq / ((f_ms + b_ms) * 1e-3),
+                    "speedup_of_this_repo_kernels": (f_ms + b_ms) / mine}
+            except Exception as exc:  # the comparison is optional; never fail the bench because of it
+                extras["reference_cuda_kernels_on_this_gpu"] = {"unavailable": repr(exc)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -426,7 +477,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"],
             "data": "synthetic", "config": workload_config(args, cfg, world),
             "hbm_gbs_per_gpu": step_gbs, "hbm_frac_step": step_gbs / peak,
-            "roofline": roof_b, "roofline_fwd": roof_f, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof_b, "roofline_fwd": roof_f, "cpu_baseline": cpu, "e2e": e2e, "extras": extras,
             "gpu_launches": launches, "kernels": {"forward": kernel_names[0], "backward": kernel_names[1]},
             "clocks": clocks,
         }

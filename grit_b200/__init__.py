@@ -9,10 +9,10 @@ host-side mirror of the reference interface (ops/).
 import sys
 
 from .ops.functions import MSDeformAttnFunction, ms_deform_attn_core_pytorch, set_deterministic  # noqa: F401
-from .ops.modules import MSDeformAttn  # noqa: F401
+from .ops.modules import MSDeformAttn, hoisted_value_proj  # noqa: F401
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "install_as_reference_ops",
-           "set_deterministic"]
+           "set_deterministic", "hoisted_value_proj"]
 
 
 def install_as_reference_ops(alias_models_ops: bool = True):

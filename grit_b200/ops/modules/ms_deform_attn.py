@@ -77,7 +77,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
+                input_padding_mask=None, value=None):
         """
         :param query                    (N, Length_{query}, C)
         :param reference_points         (N, Length_{query}, n_levels, 2) in [0, 1], top-left (0,0), bottom-right (1,1),
@@ -86,6 +86,10 @@ class MSDeformAttn(nn.Module):
         :param input_spatial_shapes     (n_levels, 2), [(H_0, W_0), ..., (H_{L-1}, W_{L-1})]
         :param input_level_start_index  (n_levels,), [0, H_0*W_0, H_0*W_0+H_1*W_1, ...]
         :param input_padding_mask       (N, sum_l H_l*W_l), True for padding elements
+        :param value                    optional (N, sum_l H_l*W_l, C): this layer's ``value_proj(input_flatten)`` computed
+                                        elsewhere (see ``hoisted_value_proj``: GRIT's six decoder layers project the SAME
+                                        memory, det_module.py:191-198, so one batched GEMM can serve all of them).  Not in
+                                        the reference signature; ``None`` gives the reference behaviour.
         :return output                  (N, Length_{query}, C)
         """
         N, Len_q, _ = query.shape
@@ -93,11 +97,12 @@ class MSDeformAttn(nn.Module):
         if self.validate_shapes:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
-        value = self.value_proj(input_flatten)
+        if value is None:
+            value = self.value_proj(input_flatten)
         if self.fused and query.is_cuda:
             # fused path: softmax, offsets/normaliser + reference points and the mask fill happen
             # inside the gather kernels; falls through to the reference-shaped path when no specialisation exists
-            value4 = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+            value4 = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
             offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
             if reference_points.shape[-1] not in (2, 4):
                 raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(
@@ -110,7 +115,7 @@ class MSDeformAttn(nn.Module):
                 return self.output_proj(output)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        value = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         attention_weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
@@ -128,3 +133,22 @@ class MSDeformAttn(nn.Module):
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, sampling_locations,
                                             attention_weights, self.im2col_step)
         return self.output_proj(output)
+
+
+def hoisted_value_proj(modules, input_flatten):
+    """``value_proj`` of several MSDeformAttn layers that read the SAME memory, as ONE GEMM.
+
+    GRIT's decoder runs six layers over an unchanged ``src`` (models/detection/det_module.py:191-198); each layer's
+    ``value_proj`` is an (N*S, C) x (C, C) GEMM that re-reads ``src``.  Concatenating the weight matrices gives one
+    (N*S, C) x (C, n*C) GEMM that reads ``src`` once.  Returns a tuple of per-layer ``value`` tensors (N, S, C), each
+    contiguous (the kernels need (N, S, M, D) contiguous, so the GEMM output is re-laid out layer-major once).
+    Pass ``value=vals[i]`` to layer i.  Gradients reach every layer's ``value_proj.weight/bias`` and ``input_flatten``
+    through autograd.
+    """
+    modules = list(modules)
+    weight = torch.cat([m.value_proj.weight for m in modules], 0)  # (n*C, C)
+    bias = torch.cat([m.value_proj.bias for m in modules], 0)
+    n_layers, c = len(modules), modules[0].d_model
+    out = F.linear(input_flatten, weight, bias)  # (N, S, n*C)
+    n, s_len, _ = input_flatten.shape
+    return out.view(n, s_len, n_layers, c).permute(2, 0, 1, 3).contiguous().unbind(0)

@@ -451,6 +451,45 @@ def test_fused_function_vs_oracle(lib, oracle, ref_dim, vdtype, D):
     assert np.abs((goff.cpu().numpy() - ref_goff)[keep]).max() / np.abs(ref_goff).max() < 1e-4
 
 
+def test_hoisted_value_proj_equals_per_layer_projection(lib):
+    """one batched value_proj GEMM for layers that share the memory == each layer projecting itself."""
+    from grit_b200 import MSDeformAttn, hoisted_value_proj
+    torch.manual_seed(3)
+    N, Lq, C, M, L, P = 2, 50, 256, 8, 4, 4
+    shapes_l = SMALL_PYR
+    S = sum(h * w for h, w in shapes_l)
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.from_numpy(helpers.level_start(shapes_l)).cuda()
+    layers = [MSDeformAttn(C, L, M, P).cuda().double() for _ in range(3)]
+    for m in layers:
+        m.fused = False
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02)
+    src = torch.randn(N, S, C, device="cuda", dtype=torch.float64, requires_grad=True)
+    query = torch.randn(N, Lq, C, device="cuda", dtype=torch.float64)
+    ref = torch.rand(N, Lq, L, 2, device="cuda", dtype=torch.float64)
+    mask = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    mask[0, ::4] = True
+
+    def run(hoist):
+        src.grad = None
+        for m in layers:
+            m.zero_grad()
+        vals = hoisted_value_proj(layers, src) if hoist else [None] * len(layers)
+        x = query
+        for m, v in zip(layers, vals):
+            x = x + m(x, ref, src, shapes, lsi, mask, value=v)
+        x.square().sum().backward()
+        return x.detach(), src.grad.clone(), [m.value_proj.weight.grad.clone() for m in layers]
+
+    out_a, gsrc_a, gw_a = run(False)
+    out_b, gsrc_b, gw_b = run(True)
+    assert max_norm_err(out_b.cpu().numpy(), out_a.cpu().numpy()) < 1e-10
+    assert max_norm_err(gsrc_b.cpu().numpy(), gsrc_a.cpu().numpy()) < 1e-10
+    for a, b in zip(gw_a, gw_b):
+        assert max_norm_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-10
+
+
 def test_mask_rows(lib):
     x = torch.randn(3, 50, 8, 32, device="cuda")
     mask = torch.rand(3, 50, device="cuda") < 0.3
