@@ -414,6 +414,20 @@ def main():
         if not torch.equal(out.cpu(), h_out):
             raise RuntimeError("e2e host path and device path disagree")
 
+    # ---- on-chip ceilings: what actually bounds a gather/scatter whose tap traffic is ~18x its HBM traffic -------------
+    if rank == 0 and not args.no_extras and dt == torch.float32 and D == 32:
+        region = torch.zeros(S * M * D, dtype=torch.float32, device=device)  # one image of value: L2-resident
+        taps = N * Lq * M * L * P * 4  # 128-byte tap lines per launch (forward gathers them, backward also reduces them)
+        for roof, which, avg_ms in ((roof_f, "gather", avg_f), (roof_b, "red", avg_b)):
+            ceiling = _lib.probe_ceiling(which, region)
+            achieved = taps / (avg_ms * 1e-3) / 1e9
+            roof["on_chip"] = {
+                "resource": {"gather": "L2->L1 gather of random 128-byte lines (LDG.E.128 stream)",
+                             "red": "L2 reduction of random 128-byte lines (REDG.E.ADD.F32x4 stream)"}[which],
+                "ceiling_glines_per_s": ceiling, "achieved_glines_per_s": achieved, "frac": achieved / ceiling,
+                "how": "msda_probe_ceiling microbenchmark, same access pattern, no arithmetic, measured in this run"}
+        del region
+
     # ---- extras (rank 0, N=1): the other location distribution and the reference's own CUDA kernels on this GPU -------
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:

@@ -65,6 +65,8 @@ def load():
         lib.msda_backward.restype = ctypes.c_int
         lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint,
                                       vp, ctypes.c_size_t, vp]
+        lib.msda_probe_ceiling.restype = ctypes.c_int
+        lib.msda_probe_ceiling.argtypes = [ctypes.c_int, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64), vp]
         lib.msda_fused_supported.restype = ctypes.c_int
         lib.msda_fused_supported.argtypes = [dimsp, ctypes.c_int, ctypes.c_int]
         lib.msda_mask_rows.restype = ctypes.c_int
@@ -190,6 +192,30 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     if rc:
         _raise(lib, rc, "msda_backward")
     return grad_value, grad_loc, grad_attn
+
+
+def probe_ceiling(which: str, scratch, iters: int = 5):
+    """G lines/s of the on-chip ceiling microbenchmark (include/msda.h: msda_probe_ceiling) over `scratch`
+    (a contiguous fp32 CUDA tensor that is overwritten when which == 'red')."""
+    lib = load()
+    code = {"gather": 0, "red": 1}[which]
+    lines = ctypes.c_int64(0)
+    best = None
+    with torch.cuda.device(scratch.device):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for i in range(iters + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = lib.msda_probe_ceiling(code, _ptr(scratch), scratch.numel() * scratch.element_size(),
+                                        ctypes.byref(lines), st)
+            e1.record()
+            if rc:
+                _raise(lib, rc, "msda_probe_ceiling")
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if i > 0:
+                best = ms if best is None else min(best, ms)
+    return lines.value / best / 1e6  # G lines/s (a line = 128 bytes)
 
 
 def fused_dims(value, sampling_offsets, reference_points):

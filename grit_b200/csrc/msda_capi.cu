@@ -842,6 +842,25 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     X(32, 4, 4)                     \
     X(64, 4, 4)
 
+int msda_probe_ceiling(int which, void *scratch, size_t scratch_bytes, int64_t *lines_out, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (!scratch || !aligned16(scratch) || scratch_bytes < (1u << 20) || !lines_out)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "msda_probe_ceiling needs a 16-byte aligned scratch buffer of >= 1 MiB");
+    if (scratch_bytes > ((size_t)1 << 36)) scratch_bytes = (size_t)1 << 36;
+    const unsigned n_lines = (unsigned)(scratch_bytes / 128);
+    const int warps = 4, blocks = device_info().sms * 32, iters = 1024;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (which == 0)
+        msda::msda_probe_gather<<<blocks, warps * 32, 0, st>>>((const float *)scratch, (float *)scratch, n_lines, iters);
+    else if (which == 1)
+        msda::msda_probe_red<<<blocks, warps * 32, 0, st>>>((float *)scratch, n_lines, iters);
+    else
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "which must be 0 (gather) or 1 (red)");
+    *lines_out = (int64_t)blocks * warps * iters * 4;
+    return check_cuda(cudaPeekAtLastError(), "msda_probe_ceiling launch");
+}
+
 int msda_fused_supported(const msda_dims *dims, int dtype, int ref_dim)
 {
     if (!dims || (dtype != MSDA_F32 && dtype != MSDA_BF16) || (ref_dim != 2 && ref_dim != 4)) return 0;

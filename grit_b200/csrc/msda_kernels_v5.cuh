@@ -359,4 +359,43 @@ __global__ void msda_det_fold(const long long *__restrict__ acc, const float *__
     }
 }
 
+// ---- on-chip ceilings (microbenchmarks used by bench.py; see profiles/r01_micro_red_gather_ceilings.txt) ---------------
+// The op moves ~18x more bytes between L2 and the SMs than its compulsory HBM traffic, so the resources that bound it
+// are the L2->L1 gather rate (forward) and the L2 reduction rate (backward).  These two kernels measure those rates
+// with the kernels' own access pattern and none of their arithmetic: uniform random 128-byte lines inside an
+// L2-resident region, four lines per warp instruction.
+__device__ __forceinline__ unsigned probe_hash(unsigned x)
+{
+    x ^= x >> 16, x *= 0x7feb352dU, x ^= x >> 15, x *= 0x846ca68bU, x ^= x >> 16;
+    return x;
+}
+
+__global__ void msda_probe_red(float *dst, unsigned n_lines, int iters)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+    const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int it = 0; it < iters; ++it) {
+        const unsigned line = probe_hash(w * 9781u + it * 4u + g) % n_lines;
+        red_add_f32x4(dst + (size_t)line * 32 + sub * 4, 1.f, 2.f, 3.f, 4.f);
+    }
+}
+
+__global__ void msda_probe_gather(const float *__restrict__ src, float *out, unsigned n_lines, int iters)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+    const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int it = 0; it < iters; it += 16) {
+        float4 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const unsigned line = probe_hash(w * 9781u + (it + k) * 4u + g) % n_lines;
+            v[k] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)line * 32 + sub * 4));
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc.x += v[k].x, acc.y += v[k].y, acc.z += v[k].z, acc.w += v[k].w;
+    }
+    if (acc.x == 123.456f) out[w] = acc.x + acc.y + acc.z + acc.w;  // keeps the loads alive, never true in practice
+}
+
 }  // namespace msda

@@ -140,6 +140,15 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
                         size_t workspace_bytes, void *cuda_stream);
 
 /*
+ * Measurement aid for bench.py: one launch of a microbenchmark with the kernels' access pattern and none of their
+ * arithmetic -- uniform random 128-byte lines inside `scratch` (make it L2-resident, e.g. one image of value),
+ * four lines per warp instruction.  which = 0: LDG.E.128 gather stream (ceiling of the forward's tap gather);
+ * which = 1: REDG.E.ADD.F32x4 stream (ceiling of the backward's grad_value scatter; scratch is accumulated into).
+ * *lines_out = lines moved by the launch; time it with CUDA events on the same stream.
+ */
+int msda_probe_ceiling(int which, void *scratch, size_t scratch_bytes, int64_t *lines_out, void *cuda_stream);
+
+/*
  * Host-buffer path (what a caller without device tensors uses; bench.py's "e2e" leg).
  * A session owns device buffers and streams sized for `max_dims`; msda_host_forward_backward copies
  * the inputs host->device image-chunk by image-chunk, runs forward+backward, and copies the four
