@@ -256,6 +256,34 @@ def test_edge_cases(lib, oracle):
     assert float(gv.abs().sum()) == 0 and gl.numel() == 0 and ga.numel() == 0
 
 
+def test_fallback_paths_large_batch_and_misaligned_storage(lib, oracle):
+    """Dispatch corner cases: batch > 65535 (beyond gridDim.y of the default kernels) and tensors whose storage is not
+    16-byte aligned must still give oracle results (older generation / generic kernels take over)."""
+    # 1) 70 000 tiny images
+    N = 70000
+    case = helpers.make_inputs(N, 1, 1, 32, [(2, 2)], 4, seed=2, dtype=np.float32)
+    got = run_kernels(lib, case, torch.float32)
+    assert "v5" not in got["fwd_kernel"] and is_specialised(got["fwd_kernel"]), got["fwd_kernel"]
+    case64 = helpers.rounded_case(case, torch.float32)
+    assert_parity(got, oracle_results(oracle, case64), case64, torch.float32, "large batch")
+    # 2) value / grad_out views that start 4 bytes into their storage
+    case = helpers.rounded_case(helpers.make_inputs(2, 21, 8, 32, SMALL_PYR, 4, seed=6), torch.float32)
+    t = helpers.to_cuda(case, torch.float32)
+
+    def shifted(x):
+        buf = torch.empty(x.numel() + 1, dtype=x.dtype, device=x.device)
+        view = buf[1:].view(x.shape)
+        view.copy_(x)
+        assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+        return view
+    v, g = shifted(t["value"]), shifted(t["grad_out"])
+    out = lib.forward(v, t["shapes"], t["level_start"], t["loc"], t["attn"])
+    assert not is_specialised(lib.last_kernel())
+    gv, gl, ga = lib.backward(v, t["shapes"], t["level_start"], t["loc"], t["attn"], g.view_as(out))
+    ref = oracle_results(oracle, case)
+    assert_parity(dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga), ref, case, torch.float32, "misaligned")
+
+
 def test_argument_checks_on_gpu(lib):
     t = helpers.to_cuda(helpers.make_inputs(1, 3, 2, 4, [(2, 2)], 1), torch.float32)
     with pytest.raises(RuntimeError, match="has to be contiguous"):
