@@ -124,6 +124,26 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: pin this rank's CPU threads (and therefore its first-touch pinned host buffers) to the NUMA node
+    its GPU hangs off, so the e2e leg's H2D/D2H copies do not cross the socket interconnect."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out  # 00000000:1b:00.0 -> 0000:1b:00.0
+        path = f"/sys/bus/pci/devices/{bus}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"bound to {len(cpus)} CPUs local to GPU {local_rank}"
+    except Exception as exc:
+        return f"no NUMA binding ({type(exc).__name__})"
+    return "no NUMA binding"
+
+
 def make_layer_inputs(torch, cfg, device, seed, loc_dist):
     """One layer's synthetic inputs, created on `device` (SURVEY.md section 8d distributions)."""
     N, M, D, P = cfg["N"], cfg["M"], cfg["D"], cfg["P"]
@@ -248,6 +268,7 @@ def main():
     import torch.distributed as dist
     from grit_b200 import _lib
 
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     lib = _lib.load()  # raises if the CUDA library is missing: no fallback
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device")
@@ -407,7 +428,7 @@ def main():
         e2e = {"value": queries_per_step * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                "path": "msda_host_forward_backward (pinned host buffers, chunked H2D/compute/D2H pipeline); "
-                       "device->host read = all four result tensors"}
+                       "device->host read = all four result tensors", "numa": numa_note}
         sess.close()
         # cheap sanity: the host path and the device path computed the same thing for the last layer set
         fwd(sets[0]); torch.cuda.synchronize()
