@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--e2e-chunk", type=int, default=None, help="images per pipeline chunk of the host-buffer path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]
@@ -406,7 +407,7 @@ def main():
         h_gl = torch.empty(gl.shape, dtype=torch.float32).pin_memory()
         h_ga = torch.empty(ga.shape, dtype=torch.float32).pin_memory()
         h_shapes, h_lsi = shapes.cpu(), lsi.cpu()
-        sess = _lib.HostSession(dims, dt, device=local_rank, images_per_chunk=max(1, N // 8))
+        sess = _lib.HostSession(dims, dt, device=local_rank, images_per_chunk=args.e2e_chunk or max(1, N // 16))
 
         def e2e_step():
             for _ in range(layers):

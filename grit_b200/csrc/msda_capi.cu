@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "msda_kernels_v3.cuh"
@@ -1025,16 +1026,17 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
 // ---- host-buffer session ---------------------------------------------------------------------------
 
 struct msda_host_session {
-    static constexpr int kSlots = 3;
+    static constexpr int kMaxSlots = 8;
+    int n_slots;  // pipeline depth: chunks in flight (H2D of one, kernels of another, D2H of a third, ...)
     msda_dims max_dims;
     int dtype;
     int device;
     int chunk;  // images per chunk
     int64_t *d_shapes, *d_lsi;
-    cudaStream_t stream[kSlots];
+    cudaStream_t stream[kMaxSlots];
     struct Slot {
         char *value, *loc, *attn, *gout, *out, *gvalue, *gloc, *gattn, *ws;
-    } slot[kSlots];
+    } slot[kMaxSlots];
     size_t ws_bytes;
 };
 
@@ -1042,7 +1044,7 @@ static void session_free(msda_host_session *s)
 {
     if (!s) return;
     cudaSetDevice(s->device);
-    for (int i = 0; i < msda_host_session::kSlots; ++i) {
+    for (int i = 0; i < msda_host_session::kMaxSlots; ++i) {
         if (s->stream[i]) cudaStreamDestroy(s->stream[i]);
         char *ptrs[] = {s->slot[i].value, s->slot[i].loc,    s->slot[i].attn, s->slot[i].gout, s->slot[i].out,
                         s->slot[i].gvalue, s->slot[i].gloc,  s->slot[i].gattn, s->slot[i].ws};
@@ -1069,6 +1071,11 @@ int msda_host_session_create(msda_host_session **session, const msda_dims *max_d
     s->dtype = dtype;
     s->device = device;
     s->chunk = images_per_chunk;
+    s->n_slots = 4;
+    if (const char *env = getenv("MSDA_HOST_SLOTS")) {
+        const int v = atoi(env);
+        if (v >= 1 && v <= msda_host_session::kMaxSlots) s->n_slots = v;
+    }
     const size_t ev = dtype_size(dtype), el = dtype == MSDA_F64 ? 8 : 4;
     const msda_dims &d = *max_dims;
     const size_t c = (size_t)images_per_chunk;
@@ -1084,7 +1091,7 @@ int msda_host_session_create(msda_host_session **session, const msda_dims *max_d
     };
     alloc((char **)&s->d_shapes, sizeof(int64_t) * 2 * d.num_levels);
     alloc((char **)&s->d_lsi, sizeof(int64_t) * d.num_levels);
-    for (int i = 0; i < msda_host_session::kSlots; ++i) {
+    for (int i = 0; i < s->n_slots; ++i) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream[i], cudaStreamNonBlocking);
         auto &k = s->slot[i];
         alloc(&k.value, n_val * ev), alloc(&k.gvalue, n_val * ev);
@@ -1125,7 +1132,7 @@ int msda_host_forward_backward(msda_host_session *s, const void *value, const in
     const size_t img_val = (size_t)(dims->spatial_size * dims->num_heads * dims->channels) * ev;
     const size_t img_pts = (size_t)(dims->num_query * dims->num_heads * dims->num_levels * dims->num_point) * el;
     const size_t img_out = (size_t)(dims->num_query * dims->num_heads * dims->channels) * ev;
-    constexpr int K = msda_host_session::kSlots;
+    const int K = s->n_slots;
 
     // level metadata: one small upload, made visible to every slot stream through an event
     cudaEvent_t meta_ready;
