@@ -96,6 +96,7 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
     if (dtype != MSDA_F32 && dtype != MSDA_BF16) return false;
     if (d->batch * d->num_query * d->num_heads >= ((int64_t)1 << 31)) return false;  // 32-bit row index
     if (d->num_heads * d->num_query >= ((int64_t)1 << 31)) return false;
+    if (d->spatial_size >= ((int64_t)1 << 27)) return false;  // pixel index is packed as pix*16 + tap mask
     return d->spatial_size * d->num_heads * d->channels < ((int64_t)1 << 31);
 }
 
@@ -457,12 +458,13 @@ int launch_fwd_v3(const msda_dims *d, const void *value, const int64_t *shapes, 
                   const void *attn, void *out, cudaStream_t st)
 {
     constexpr int E = msda::Chunk<T>::E;
-    const bool big = g_v3_threads.load() >= 1024;
+    const int th = g_v3_threads.load();
 #define X(DD, LL, PP)                                                                                     \
     if constexpr (v2_ok<DD, LL, PP, E>()) {                                                               \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                        \
-            return big ? fwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, out, st)    \
-                       : fwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, out, st);    \
+            return th >= 1024  ? fwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, out, st) \
+                   : th >= 768 ? fwd_v3_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, out, st)  \
+                               : fwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, out, st); \
     }
     MSDA_FOR_EACH_V3_SPEC(X)
 #undef X

@@ -150,6 +150,8 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
                 float acc[E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) acc[e] = 0.f;
+                // warp-uniform fast path: every tap of every point of the row is inside its map
+                const bool all_valid = __all_sync(0xffffffffu, (mine.pm & 15) == 15);
 #pragma unroll
                 for (int it = 0; it < PPG; ++it) {
                     const int pt = it * G + g;
@@ -162,24 +164,39 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
                     const int sb = plan.sbase[l];
                     const int pix = pm >> 4;
                     float v0[E], v1[E], v2[E], v3[E];
+                    if (sb != kNotStaged) {  // taps from the staged plane: LDS.128, 32-bit offsets
+                        const T *s0 = stage + (sb + pix * D + sub * E);
+                        const int so1 = D, so2 = W * D, so3 = W * D + D;
+                        if (all_valid) {
+                            Chunk<T>::load_shared(s0, v0);
+                            Chunk<T>::load_shared(s0 + so1, v1);
+                            Chunk<T>::load_shared(s0 + so2, v2);
+                            Chunk<T>::load_shared(s0 + so3, v3);
+                        } else {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
-                    if (sb != kNotStaged) {
-                        const T *s0 = stage + sb + pix * D + sub * E;
-                        const T *s1 = s0 + W * D;
-                        if (pm & 1) Chunk<T>::load_shared(s0, v0);
-                        if (pm & 2) Chunk<T>::load_shared(s0 + D, v1);
-                        if (pm & 4) Chunk<T>::load_shared(s1, v2);
-                        if (pm & 8) Chunk<T>::load_shared(s1 + D, v3);
-                    } else {
-                        const T *p0 = vimg + (int64_t)pix * MD + sub * E;
-                        const T *p1 = p0 + (int64_t)W * MD;
-                        if (pm & 1) Chunk<T>::load(p0, v0);
-                        if (pm & 2) Chunk<T>::load(p0 + MD, v1);
-                        if (pm & 4) Chunk<T>::load(p1, v2);
-                        if (pm & 8) Chunk<T>::load(p1 + MD, v3);
+                            for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+                            if (pm & 1) Chunk<T>::load_shared(s0, v0);
+                            if (pm & 2) Chunk<T>::load_shared(s0 + so1, v1);
+                            if (pm & 4) Chunk<T>::load_shared(s0 + so2, v2);
+                            if (pm & 8) Chunk<T>::load_shared(s0 + so3, v3);
+                        }
+                    } else {  // taps from L2: one IMAD.WIDE per address
+                        const int o0 = pix * MD + sub * E, o1 = o0 + MD, o2 = o0 + W * MD, o3 = o2 + MD;
+                        if (all_valid) {
+                            Chunk<T>::load(vimg + o0, v0);
+                            Chunk<T>::load(vimg + o1, v1);
+                            Chunk<T>::load(vimg + o2, v2);
+                            Chunk<T>::load(vimg + o3, v3);
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
+                            if (pm & 1) Chunk<T>::load(vimg + o0, v0);
+                            if (pm & 2) Chunk<T>::load(vimg + o1, v1);
+                            if (pm & 4) Chunk<T>::load(vimg + o2, v2);
+                            if (pm & 8) Chunk<T>::load(vimg + o3, v3);
+                        }
                     }
-                    const float ah = a * (1.f - lh), al = a * lh, hw = 1.f - lw;
+                    const float ah = a - a * lh, al = a * lh, hw = 1.f - lw;
                     const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
 #pragma unroll
                     for (int e = 0; e < E; ++e)

@@ -518,6 +518,44 @@ def test_hoisted_value_proj_equals_per_layer_projection(lib):
         assert max_norm_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-10
 
 
+def test_forward_backward_capture_in_a_cuda_graph(lib, oracle):
+    """The C-ABI entry points only enqueue work on the caller's stream (no sync, no allocation, no host read of the
+    level tensors), so a forward+backward pair can be captured once and replayed as a CUDA graph."""
+    import ctypes
+    case = helpers.rounded_case(helpers.make_inputs(2, 150, 8, 32, SMALL_PYR, 4, seed=12), torch.float32)
+    t = helpers.to_cuda(case, torch.float32)
+    N, S, M, D = t["value"].shape
+    Lq, L, P = 150, 4, 4
+    out = torch.empty(N, Lq, M * D, device="cuda")
+    gv, gl, ga = torch.empty_like(t["value"]), torch.empty_like(t["loc"]), torch.empty_like(t["attn"])
+    dims = lib.MsdaDims(N, S, M, D, L, Lq, P)
+    raw = lib.load()
+    p = lib._ptr
+
+    def enqueue(stream):
+        st = ctypes.c_void_p(stream.cuda_stream)
+        assert raw.msda_forward(p(t["value"]), p(t["shapes"]), p(t["level_start"]), p(t["loc"]), p(t["attn"]), p(out),
+                                ctypes.byref(dims), 0, 0, st) == 0
+        assert raw.msda_backward(p(t["value"]), p(t["shapes"]), p(t["level_start"]), p(t["loc"]), p(t["attn"]),
+                                 p(t["grad_out"]), p(gv), p(gl), p(ga), ctypes.byref(dims), 0,
+                                 lib.FLAG_ZERO_GRAD_VALUE, None, 0, st) == 0
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        enqueue(side)  # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        enqueue(side)
+    out.zero_(), gv.fill_(7.0), gl.zero_(), ga.zero_()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    ref = oracle_results(oracle, case)
+    assert_parity(dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga), ref, case, torch.float32, "graph replay")
+
+
 def test_mask_rows(lib):
     x = torch.randn(3, 50, 8, 32, device="cuda")
     mask = torch.rand(3, 50, device="cuda") < 0.3
