@@ -284,6 +284,38 @@ def test_fallback_paths_large_batch_and_misaligned_storage(lib, oracle):
     assert_parity(dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga), ref, case, torch.float32, "misaligned")
 
 
+@pytest.mark.parametrize("M,D,shapes,P", [(6, 32, SMALL_PYR, 4), (3, 64, SMALL_PYR, 4), (5, 32, [(9, 14)], 8),
+                                          (12, 16, SMALL_PYR, 4)])
+def test_head_counts_that_are_not_powers_of_two(lib, oracle, M, D, shapes, P):
+    """The default kernels derive the head index with a mask when M is a power of two and with a modulo otherwise."""
+    case = helpers.rounded_case(helpers.make_inputs(3, 41, M, D, shapes, P, seed=M * 7 + D), torch.float32)
+    got = run_kernels(lib, case, torch.float32)
+    assert is_specialised(got["fwd_kernel"]) and is_specialised(got["bwd_kernel"])
+    assert_parity(got, oracle_results(oracle, case), case, torch.float32, f"M={M}")
+
+
+def test_non_finite_and_extreme_coordinates(lib, oracle):
+    """+-inf, NaN, +-1e30 and denormal coordinates: skipped points contribute nothing, nothing becomes NaN, and the
+    rest of the row is unaffected (specialised fp32 kernels, fused kernels excluded: they take raw offsets)."""
+    case = helpers.make_inputs(2, 40, 8, 32, SMALL_PYR, 4, seed=77)
+    loc = case["loc"]
+    loc[0, 0, :, 0, 0] = np.inf
+    loc[0, 1, :, 1, 1] = -np.inf
+    loc[0, 2, :, 2, 2] = np.nan
+    loc[0, 3, :, 3, 3] = 1e30
+    loc[0, 4, :, 0, 1] = -1e30
+    loc[0, 5, :, 1, 2] = 1e-42
+    case["attn"][0, 2, :, 2, 2] = np.nan  # weight of a skipped point is never read
+    case = helpers.rounded_case(case, torch.float32)
+    finite = dict(case)
+    finite["loc"] = np.where(np.isfinite(case["loc"]), case["loc"], 50.0)   # oracle: any far-outside value
+    finite["attn"] = np.nan_to_num(case["attn"], nan=0.0)
+    got = run_kernels(lib, case, torch.float32)
+    for k in ("out", "grad_value", "grad_loc", "grad_attn"):
+        assert torch.isfinite(got[k]).all(), k
+    assert_parity(got, oracle_results(oracle, finite), finite, torch.float32, "non-finite coordinates")
+
+
 def test_argument_checks_on_gpu(lib):
     t = helpers.to_cuda(helpers.make_inputs(1, 3, 2, 4, [(2, 2)], 1), torch.float32)
     with pytest.raises(RuntimeError, match="has to be contiguous"):
