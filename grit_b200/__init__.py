@@ -8,11 +8,12 @@ host-side mirror of the reference interface (ops/).
 """
 import sys
 
-from .ops.functions import MSDeformAttnFunction, ms_deform_attn_core_pytorch, set_deterministic  # noqa: F401
+from .ops.functions import (MSDeformAttnFunction, ms_deform_attn_core_pytorch, pack_levels,  # noqa: F401
+                            set_deterministic)
 from .ops.modules import MSDeformAttn, hoisted_value_proj  # noqa: F401
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "install_as_reference_ops",
-           "set_deterministic", "hoisted_value_proj"]
+           "set_deterministic", "hoisted_value_proj", "pack_levels"]
 
 
 def install_as_reference_ops(alias_models_ops: bool = True):

@@ -65,6 +65,9 @@ def load():
         lib.msda_backward.restype = ctypes.c_int
         lib.msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint,
                                       vp, ctypes.c_size_t, vp]
+        lib.msda_pack_levels.restype = ctypes.c_int
+        lib.msda_pack_levels.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
+                                         ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int, ctypes.c_int, vp]
         lib.msda_probe_ceiling.restype = ctypes.c_int
         lib.msda_probe_ceiling.argtypes = [ctypes.c_int, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64), vp]
         lib.msda_fused_supported.restype = ctypes.c_int
@@ -192,6 +195,31 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     if rc:
         _raise(lib, rc, "msda_backward")
     return grad_value, grad_loc, grad_attn
+
+
+def pack_levels(levels, memory=None, unpack: bool = False):
+    """levels: list of contiguous CUDA (N, C, H_l, W_l) tensors; memory: (N, sum H_l*W_l, C).
+    unpack=False writes `memory` from the levels (allocating it when None); unpack=True writes the levels from it."""
+    lib = load()
+    n, c = levels[0].shape[:2]
+    hw = [int(t.shape[2] * t.shape[3]) for t in levels]
+    for t in levels:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == levels[0].dtype and tuple(t.shape[:2]) == (n, c)):
+            raise RuntimeError("pack_levels expects contiguous CUDA (N, C, H, W) tensors of one dtype")
+    if levels[0].dtype not in _DTYPE_CODE:
+        raise RuntimeError(f"pack_levels not implemented for {levels[0].dtype}")
+    if memory is None:
+        memory = torch.empty((n, sum(hw), c), dtype=levels[0].dtype, device=levels[0].device)
+    if not memory.is_contiguous() or tuple(memory.shape) != (n, sum(hw), c) or memory.dtype != levels[0].dtype:
+        raise RuntimeError("memory must be a contiguous (N, S, C) tensor of the levels' dtype")
+    ptrs = (ctypes.c_void_p * len(levels))(*[t.data_ptr() for t in levels])
+    hws = (ctypes.c_int64 * len(levels))(*hw)
+    with torch.cuda.device(memory.device):
+        rc = lib.msda_pack_levels(ptrs, hws, len(levels), n, c, _ptr(memory), _DTYPE_CODE[memory.dtype],
+                                  1 if unpack else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_pack_levels")
+    return memory
 
 
 def probe_ceiling(which: str, scratch, iters: int = 5):

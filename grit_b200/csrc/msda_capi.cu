@@ -845,6 +845,47 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     X(32, 4, 4)                     \
     X(64, 4, 4)
 
+int msda_pack_levels(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch, int64_t channels,
+                     void *memory, int dtype, int unpack, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (!level_ptrs || !level_hw || !memory) return fail(MSDA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (num_levels < 1 || num_levels > 8) return fail(MSDA_ERR_UNSUPPORTED, "msda_pack_levels supports 1..8 levels");
+    if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F64)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "unknown dtype %d", dtype);
+    if (batch <= 0 || channels <= 0) return MSDA_OK;
+    if (batch > 65535) return fail(MSDA_ERR_UNSUPPORTED, "batch > 65535");
+    msda::PackArgs a;
+    a.num_levels = num_levels;
+    int64_t S = 0, tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        if (!level_ptrs[l] || level_hw[l] <= 0 || level_hw[l] > 0x7fffffff)
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "bad level %d", l);
+        a.level[l] = level_ptrs[l];
+        a.hw[l] = (int)level_hw[l];
+        a.start[l] = (int)S;
+        a.tile_start[l] = (int)tiles;
+        S += level_hw[l];
+        tiles += (level_hw[l] + 31) / 32;
+    }
+    a.tile_start[num_levels] = (int)tiles;
+    if (S > 0x7fffffff || tiles > 0x7fffffff) return fail(MSDA_ERR_INVALID_ARGUMENT, "pyramid too large");
+    const dim3 grid((unsigned)tiles, (unsigned)((channels + 31) / 32), (unsigned)batch);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+#define LAUNCH(T)                                                                                        \
+    (unpack ? msda::msda_pack_levels<T, false><<<grid, 256, 0, st>>>(a, (T *)memory, (int)channels, (int)S) \
+            : msda::msda_pack_levels<T, true><<<grid, 256, 0, st>>>(a, (T *)memory, (int)channels, (int)S))
+    if (dtype == MSDA_F32)
+        LAUNCH(float);
+    else if (dtype == MSDA_F64)
+        LAUNCH(double);
+    else
+        LAUNCH(__nv_bfloat16);
+#undef LAUNCH
+    ++tl_launches;
+    return check_cuda(cudaPeekAtLastError(), "msda_pack_levels launch");
+}
+
 int msda_probe_ceiling(int which, void *scratch, size_t scratch_bytes, int64_t *lines_out, void *cuda_stream)
 {
     tl_error[0] = 0;

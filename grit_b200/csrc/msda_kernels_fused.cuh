@@ -191,4 +191,58 @@ __global__ void msda_mask_rows(T *__restrict__ data, const unsigned char *__rest
     }
 }
 
+// ---- level packing --------------------------------------------------------------------------------
+// prepare_od_inputs (models/detection/det_module.py:146-155) turns the per-level NCHW outputs of input_proj into the
+// (N, S, C) memory the op reads: `src.flatten(2).transpose(1, 2)` per level, then `torch.cat` -- a strided-read copy.
+// msda_pack_levels does it in one launch with a 32x32 shared-memory tile transpose (coalesced 128-byte reads along
+// H*W and writes along C); PACK=false is the adjoint (grad of memory -> per-level NCHW grads).
+struct PackArgs {
+    void *level[8];          // NCHW level tensors (sources when packing, destinations when unpacking)
+    int hw[8];               // H_l * W_l
+    int start[8];            // level_start_index
+    int tile_start[9];       // prefix sum of tiles per level; tile_start[L] = total
+    int num_levels;
+};
+
+template <typename T, bool PACK>
+__global__ void __launch_bounds__(256)
+msda_pack_levels(PackArgs args, T *__restrict__ memory, int C, int S)
+{
+    __shared__ T tile[32][33];
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * 32;
+    int l = 0;
+    while (l + 1 < args.num_levels && (int)blockIdx.x >= args.tile_start[l + 1]) ++l;
+    const int p0 = ((int)blockIdx.x - args.tile_start[l]) * 32;  // first pixel of this tile inside level l
+    const int hw = args.hw[l];
+    T *lvl = reinterpret_cast<T *>(args.level[l]) + (int64_t)n * C * hw;  // (C, hw) plane of image n
+    T *mem = memory + ((int64_t)n * S + args.start[l]) * C;              // (hw, C) rows of image n, level l
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;              // 32 x 8 threads
+    if (PACK) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {  // read (c, p) with p fastest
+            const int c = c0 + ty + j, p = p0 + tx;
+            if (c < C && p < hw) tile[ty + j][tx] = lvl[(int64_t)c * hw + p];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {  // write (p, c) with c fastest
+            const int p = p0 + ty + j, c = c0 + tx;
+            if (c < C && p < hw) mem[(int64_t)p * C + c] = tile[tx][ty + j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const int p = p0 + ty + j, c = c0 + tx;
+            if (c < C && p < hw) tile[tx][ty + j] = mem[(int64_t)p * C + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const int c = c0 + ty + j, p = p0 + tx;
+            if (c < C && p < hw) lvl[(int64_t)c * hw + p] = tile[ty + j][tx];
+        }
+    }
+}
+
 }  // namespace msda

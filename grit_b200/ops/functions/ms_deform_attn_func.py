@@ -123,6 +123,38 @@ class MSDeformAttnFusedFunction(Function):
         return grad_value, None, None, grad_offs, grad_logits, grad_ref, None
 
 
+class PackLevelsFunction(Function):
+    """Multi-level NCHW feature maps -> the (N, S, C) memory the op reads, in one tiled-transpose launch
+    (SURVEY.md 8f-3).  Same result as the reference's ``torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)``
+    (models/detection/det_module.py:146-155); the backward is the adjoint scatter back to per-level NCHW gradients."""
+
+    @staticmethod
+    def forward(ctx, *levels):
+        levels = [t.contiguous() for t in levels]
+        ctx.shapes = [tuple(t.shape) for t in levels]
+        return _lib.pack_levels(levels)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_memory):
+        grads = [torch.empty(shape, dtype=grad_memory.dtype, device=grad_memory.device) for shape in ctx.shapes]
+        _lib.pack_levels(grads, grad_memory.contiguous(), unpack=True)
+        return tuple(grads)
+
+
+def pack_levels(levels):
+    """``memory, spatial_shapes, level_start_index`` from a list of (N, C, H_l, W_l) feature maps -- the tensors
+    prepare_od_inputs builds (models/detection/det_module.py:146-158); shapes/starts are int64 tensors on the device."""
+    memory = PackLevelsFunction.apply(*levels)
+    hw = [(int(t.shape[2]), int(t.shape[3])) for t in levels]
+    spatial_shapes = torch.as_tensor(hw, dtype=torch.long, device=memory.device)
+    starts = [0]
+    for h, w in hw[:-1]:
+        starts.append(starts[-1] + h * w)
+    level_start_index = torch.as_tensor(starts, dtype=torch.long, device=memory.device)
+    return memory, spatial_shapes, level_start_index
+
+
 def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
     """Debug/test helper with the reference's name and signature (reference :41-61): the same function written in
     plain differentiable PyTorch (explicit four-tap gathers instead of ``F.grid_sample``).  Works on any device and

@@ -140,6 +140,15 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
                         size_t workspace_bytes, void *cuda_stream);
 
 /*
+ * Level packing -- SURVEY.md section 8f-3.  Replaces the flatten/transpose/cat of prepare_od_inputs
+ * (models/detection/det_module.py:146-155): `level_ptrs[l]` is the contiguous NCHW tensor (N, C, H_l, W_l) of level l,
+ * `level_hw[l]` = H_l*W_l (host ints), `memory` is (N, sum_l H_l*W_l, C).  unpack = 0: levels -> memory;
+ * unpack = 1: memory -> levels (the adjoint, i.e. the backward of the packing).  One launch, tiled transpose.
+ */
+int msda_pack_levels(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch, int64_t channels,
+                     void *memory, int dtype, int unpack, void *cuda_stream);
+
+/*
  * Measurement aid for bench.py: one launch of a microbenchmark with the kernels' access pattern and none of their
  * arithmetic -- uniform random 128-byte lines inside `scratch` (make it L2-resident, e.g. one image of value),
  * four lines per warp instruction.  which = 0: LDG.E.128 gather stream (ceiling of the forward's tap gather);

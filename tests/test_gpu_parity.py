@@ -588,6 +588,29 @@ def test_forward_backward_capture_in_a_cuda_graph(lib, oracle):
     assert_parity(dict(out=out, grad_value=gv, grad_loc=gl, grad_attn=ga), ref, case, torch.float32, "graph replay")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+def test_pack_levels_matches_flatten_transpose_cat(lib, dtype):
+    """one tiled-transpose launch == the reference's flatten(2).transpose(1,2) + cat, and its backward
+    is the exact adjoint (bit-identical: pure data movement)."""
+    import grit_b200
+    torch.manual_seed(0)
+    N, C = 3, 72  # C not a multiple of 32, level sizes not multiples of 32
+    hw = [(13, 21), (7, 11), (4, 6), (1, 3)]
+    levels = [torch.randn(N, C, h, w, device="cuda").to(dtype).requires_grad_(True) for h, w in hw]
+    memory, shapes, lsi = grit_b200.pack_levels(levels)
+    want = torch.cat([t.flatten(2).transpose(1, 2) for t in levels], 1)
+    assert torch.equal(memory, want)
+    assert shapes.tolist() == [list(x) for x in hw] and lsi.tolist() == [0, 273, 350, 374]
+    g = torch.randn_like(memory)
+    memory.backward(g)
+    got = [t.grad.clone() for t in levels]
+    for t in levels:
+        t.grad = None
+    want.backward(g)
+    for a, t in zip(got, levels):
+        assert torch.equal(a, t.grad)
+
+
 def test_mask_rows(lib):
     x = torch.randn(3, 50, 8, 32, device="cuda")
     mask = torch.rand(3, 50, device="cuda") < 0.3
