@@ -45,6 +45,37 @@ __global__ void k_tma(float* dst, unsigned n_lines, int iters)
     if (lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// (d) both egress paths at once: even warps use register reds, odd warps the TMA bulk reduction
+__global__ void k_mixed(float* dst, unsigned n_lines, int iters, int tma_every)
+{
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7, warp = threadIdx.x >> 5;
+    const unsigned w = blockIdx.x * (blockDim.x >> 5) + warp;
+    float* wbuf = smem + warp * 2 * 128;
+    for (int it = 0; it < iters; ++it) {
+        if (tma_every > 0 && (it % tma_every) == 0) {
+            float* buf = wbuf + ((it / tma_every) & 1) * 128;
+            if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            *reinterpret_cast<float4*>(buf + g * 32 + sub * 4) = make_float4(1.f, 2.f, 3.f, 4.f);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane < 4) {
+                const unsigned line = hash32(w * 9781u + it * 4u + lane) % n_lines;
+                float* p = dst + (size_t)line * 32;
+                const unsigned s = (unsigned)__cvta_generic_to_shared(buf + lane * 32);
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" ::"l"(p), "r"(s) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            const unsigned line = hash32(w * 9781u + it * 4u + g) % n_lines;
+            float* p = dst + (size_t)line * 32 + sub * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+        }
+    }
+    if (lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // (c) pure gather: LDG.E.128 of random 128-byte lines (4 per warp instruction, 16 instructions in flight per lane),
 //     the access pattern of the forward without any of its arithmetic
 __global__ void k_gather(const float* __restrict__ src, float* out, unsigned n_lines, int iters)
@@ -91,6 +122,28 @@ int main()
         cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
         printf("cp.reduce.bulk  : %.3f ms  %.1f G lines/s  %.2f TB/s payload  (%s)\n", ms, lines / ms / 1e6, lines * 128 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
+    }
+    // (e) where is the reduction ceiling: SM egress or L2?  Same stream from 37 / 74 / 148 SMs (one 1024-thread CTA each)
+    for (int sms = 37; sms <= 148; sms *= 2) {
+        const int it2 = 4096;
+        const double lines2 = (double)sms * 32 * it2 * 4;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEventRecord(e0);
+            k_red<<<sms, 1024>>>(dst, n_lines, it2);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        printf("red.v4.f32 from %3d SMs: %.3f ms  %.1f G lines/s  = %.2f lines/us/SM\n", sms, ms, lines2 / ms / 1e6, lines2 / ms / 1e3 / sms);
+    }
+    for (int every = 2; every <= 4; ++every)
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        k_mixed<<<blocks, warps_per_block * 32, warps_per_block * 2 * 128 * sizeof(float)>>>(dst, n_lines, iters, every);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        printf("mixed 1/%d via TMA: %.3f ms  %.1f G lines/s  %.2f TB/s payload  (%s)\n", every, ms, lines / ms / 1e6, lines * 128 / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
     }
     for (int rep = 0; rep < 3; ++rep) {
         cudaEventRecord(e0);
