@@ -479,6 +479,26 @@ def main():
         f_ms, b_ms = time_pair(alt, fwd, bwd_zero)
         extras[f"loc_dist_{other}"] = {"fwd_ms": f_ms, "bwd_ms": b_ms, "queries_per_s": N * Lq / ((f_ms + b_ms) * 1e-3)}
         del alt
+        # the other BASELINE.json configs, one quick forward/backward timing each (public API, device tensors)
+        for name in ("grit_encoder_384x640", "grit_decoder_384x640_bf16", "grit_decoder_800x1333_bf16"):
+            if name == args.workload:
+                continue
+            c2 = WORKLOADS[name]
+            x = make_layer_inputs(torch, c2, device, 5, "uniform")
+            sh = torch.tensor(c2["shapes"], dtype=torch.int64, device=device)
+            ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+            f_ms, b_ms = time_pair(x, lambda s_: _lib.forward(s_["value"], sh, ls, s_["loc"], s_["attn"]),
+                                   lambda s_: _lib.backward(s_["value"], sh, ls, s_["loc"], s_["attn"], s_["gout"]))
+            S2 = sum(h * w for h, w in c2["shapes"])
+            Lq2 = c2["Lq"] or S2
+            fb, bb = algorithmic_bytes(c2["N"], S2, Lq2, c2["M"], c2["D"], len(c2["shapes"]), c2["P"],
+                                       4 if c2["dtype"] == "f32" else 2)
+            extras[name] = {"dtype": c2["dtype"], "N": c2["N"], "Lq": Lq2, "S": S2, "D": c2["D"],
+                            "fwd_ms": f_ms, "bwd_ms_incl_alloc_zero_fold": b_ms,
+                            "fwd_queries_per_s": c2["N"] * Lq2 / (f_ms * 1e-3),
+                            "fwd_bwd_queries_per_s": c2["N"] * Lq2 / ((f_ms + b_ms) * 1e-3),
+                            "fwd_hbm_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_hbm_frac": bb / (b_ms * 1e-3) / 1e9 / peak}
+            del x
         ref_so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttentionRef.so")
         if os.path.exists(ref_so) and dt == torch.float32:
             try:
