@@ -116,7 +116,10 @@ class MSDeformAttnFusedFunction(Function):
                 grad_ref = (grad_offs * normalizer[None, None, None, :, None, :]).sum(dim=(2, 4))
             else:  # loc = ref.xy + off / P * ref.wh * 0.5
                 scale = ref[:, :, None, :, None, 2:] * (0.5 / n_points)
-                grad_loc = grad_offs / scale
+                # (a zero-size reference box collapses every sample onto its centre and carries no offset gradient to
+                #  recover grad_loc from; its reference-point gradient is reported as 0 instead of NaN)
+                grad_loc = torch.where(scale != 0, grad_offs / torch.where(scale != 0, scale, torch.ones_like(scale)),
+                                       torch.zeros_like(grad_offs))
                 grad_xy = grad_loc.sum(dim=(2, 4))
                 grad_wh = (grad_loc * offsets * (0.5 / n_points)).sum(dim=(2, 4))
                 grad_ref = torch.cat([grad_xy, grad_wh], -1)
