@@ -269,7 +269,8 @@ def main():
     import torch.distributed as dist
     from grit_b200 import _lib
 
-    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("MSDA_BENCH_NUMA_BIND", "0") == "1" \
+        else None
     lib = _lib.load()  # raises if the CUDA library is missing: no fallback
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device")
