@@ -17,7 +17,7 @@ What is timed
   e2e        the same step through msda_host_forward_backward: pinned HOST buffers in, HOST buffers out, copies timed.
   cpu_baseline / --impl reference
              the reference's CPU path (F.grid_sample composition, restated in oracle/msda_ref_torch.py) on the host
-             cores, on a bounded sample (one 800x1333 image per step).
+             cores, on a bounded sample (two 800x1333 images per step).
 """
 import argparse
 import json
@@ -209,7 +209,7 @@ def run_reference_arm(args, cfg, rank):
     threads = os.cpu_count() or 1
     S = sum(h * w for h, w in cfg["shapes"])
     Lq = cfg["Lq"] or S
-    qps, sec_per_step, sample = cpu_reference_pass(torch, cfg, 1, threads, args.steps, args.warmup, args.loc_dist)
+    qps, sec_per_step, sample = cpu_reference_pass(torch, cfg, 2, threads, args.steps, args.warmup, args.loc_dist)
     line = {
         "impl": "reference", "metric": "msda_fwd_bwd_queries_per_sec", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
@@ -500,6 +500,45 @@ def main():
                             "fwd_bwd_queries_per_s": c2["N"] * Lq2 / ((f_ms + b_ms) * 1e-3),
                             "fwd_hbm_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_hbm_frac": bb / (b_ms * 1e-3) / 1e9 / peak}
             del x
+        # the module around the op (4 Linears + pre-op arithmetic + op), reference-shaped path vs fused kernels (8f-1)
+        if dt == torch.float32:
+            try:
+                from grit_b200 import MSDeformAttn
+                nm = min(N, 4)
+                torch.manual_seed(0)
+                mod = MSDeformAttn(M * D, L, M, P).to(device)
+                mod.validate_shapes = False
+                with torch.no_grad():
+                    mod.sampling_offsets.weight.normal_(0, 0.01)
+                    mod.attention_weights.weight.normal_(0, 0.1)
+                mq = torch.randn(nm, Lq, M * D, device=device, requires_grad=True)
+                ms_ = torch.randn(nm, S, M * D, device=device, requires_grad=True)
+                mr = torch.rand(nm, Lq, L, 2, device=device)
+                mg = torch.randn(nm, Lq, M * D, device=device)
+                mm = torch.zeros(nm, S, dtype=torch.bool, device=device)
+                mm[:, ::10] = True
+                res = {}
+                for fused in (False, True):
+                    mod.fused = fused
+
+                    def mstep(_):
+                        mq.grad = ms_.grad = None
+                        mod.zero_grad(set_to_none=True)
+                        mod(mq, mr, ms_, shapes, lsi, mm).backward(mg)
+                    for _ in range(2):
+                        mstep(None)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record()
+                    for _ in range(3):
+                        mstep(None)
+                    b.record()
+                    torch.cuda.synchronize()
+                    res["fused" if fused else "reference_shaped"] = a.elapsed_time(b) / 3
+                extras["module_fwd_bwd_ms"] = dict(res, images=nm, note="MSDeformAttn module incl. its four fp32 Linears "
+                                                   "(cuBLAS, torch default precision), padding mask on 10% of pixels")
+                del mod, mq, ms_, mr, mg, mm
+            except Exception as exc:
+                extras["module_fwd_bwd_ms"] = {"unavailable": repr(exc)[:200]}
         ref_so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttentionRef.so")
         if os.path.exists(ref_so) and dt == torch.float32:
             try:
