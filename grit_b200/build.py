@@ -4,6 +4,7 @@ Replaces the reference's models/ops/setup.py:23-60 (a torch CUDAExtension that r
 without a visible GPU): here the product is a plain C-ABI ``libmsda_b200.so`` with no torch or
 pybind dependency, so one nvcc invocation is the whole build.
 """
+import glob
 import os
 import shutil
 import subprocess
@@ -13,7 +14,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 LIB_NAME = "libmsda_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 SOURCES = [os.path.join(PKG_DIR, "csrc", "msda_capi.cu")]
-HEADERS = [os.path.join(PKG_DIR, "csrc", "msda_kernels.cuh"), os.path.join(REPO_DIR, "include", "msda.h")]
+HEADERS = sorted(glob.glob(os.path.join(PKG_DIR, "csrc", "*.cuh"))) + [os.path.join(REPO_DIR, "include", "msda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
