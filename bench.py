@@ -389,11 +389,21 @@ def main():
             traffic = json.load(open(tpath)).get(args.workload, {}).get(kb)
         except Exception:
             traffic = None
+    med = lambda xs: sorted(xs)[len(xs) // 2]
     roof_b = {"kernel": kb, "bound": "hbm", "achieved": bwd_b / (avg_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
               "frac": bwd_b / (avg_b * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic_bytes": bwd_b,
-              "avg_launch_ms": avg_b, "peak_source": peak_src}
+              "avg_launch_ms": avg_b, "median_launch_ms": med(bwd_ms), "min_launch_ms": min(bwd_ms),
+              "launches_timed": len(bwd_ms), "peak_source": peak_src}
+    ftraffic = None
+    if os.path.exists(tpath):
+        try:
+            ftraffic = json.load(open(tpath)).get(args.workload, {}).get(kf)
+        except Exception:
+            ftraffic = None
     roof_f = {"kernel": kf, "bound": "hbm", "achieved": fwd_b / (avg_f * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-              "frac": fwd_b / (avg_f * 1e-3) / 1e9 / peak, "algorithmic_bytes": fwd_b, "avg_launch_ms": avg_f}
+              "frac": fwd_b / (avg_f * 1e-3) / 1e9 / peak, "traffic": ftraffic, "algorithmic_bytes": fwd_b,
+              "avg_launch_ms": avg_f, "median_launch_ms": med(fwd_ms), "min_launch_ms": min(fwd_ms),
+              "launches_timed": len(fwd_ms)}
     step_gbs = (fwd_b + bwd_b) * layers * args.steps / (elapsed_ms * 1e-3) / 1e9  # per GPU
 
     # ---- end to end: pinned host buffers through the C ABI's host entry point --------------------------------------
