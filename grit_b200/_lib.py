@@ -29,6 +29,24 @@ class MsdaDims(ctypes.Structure):
 
 _lib = None
 _lock = threading.Lock()
+_NVTX = os.environ.get("GRIT_B200_NVTX", "0") not in ("", "0")
+
+
+class _nvtx_range:
+    """NVTX range around a library call when GRIT_B200_NVTX=1 (shows up in nsys / ncu --nvtx timelines); a no-op
+    otherwise.  The reference has no tracing hooks at all."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def library_path() -> str:
@@ -161,7 +179,7 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     dims = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _nvtx_range("msda_forward"):
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.msda_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
                               _ptr(attn_weight), _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], flags,
@@ -185,7 +203,7 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     else:
         grad_value = torch.zeros_like(value)
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _nvtx_range("msda_backward"):
         stream = torch.cuda.current_stream().cuda_stream
         rc = lib.msda_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
                                _ptr(attn_weight), _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc),
@@ -290,7 +308,7 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
     dims = fused_dims(value, sampling_offsets, reference_points)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _nvtx_range("msda_fused_forward"):
         rc = lib.msda_fused_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
                                     _ptr(attn_logits), _ptr(reference_points), int(reference_points.shape[-1]),
                                     _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], 0,
@@ -314,7 +332,7 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
     else:
         grad_value = torch.zeros_like(value)
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device):
+    with torch.cuda.device(value.device), _nvtx_range("msda_fused_backward"):
         rc = lib.msda_fused_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
                                      _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
                                      int(reference_points.shape[-1]), _ptr(grad_output), _ptr(grad_value),
