@@ -113,6 +113,11 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
     X(32, 1, 8)               \
     X(64, 1, 8)
 
+// first-generation kernels are kept for A/B only: flagship shapes
+#define MSDA_FOR_EACH_V1_SPEC(X) \
+    X(32, 4, 4)                  \
+    X(64, 4, 4)
+
 template <typename T>
 const char *tname();
 template <>
@@ -135,7 +140,7 @@ bool launch_fwd_vec(const msda_dims *d, const Geometry &g, const void *value, co
             return true;                                                                                       \
         }                                                                                                      \
     }
-    MSDA_FOR_EACH_SPEC(X)
+    MSDA_FOR_EACH_V1_SPEC(X)
 #undef X
     return false;
 }
@@ -158,7 +163,7 @@ bool launch_bwd_vec(const msda_dims *d, const Geometry &g, const void *value, co
             return true;                                                                                       \
         }                                                                                                      \
     }
-    MSDA_FOR_EACH_SPEC(X)
+    MSDA_FOR_EACH_V1_SPEC(X)
 #undef X
     return false;
 }
