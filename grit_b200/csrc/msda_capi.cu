@@ -343,6 +343,20 @@ void bwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes,
              det_scale ? ",deterministic" : "");
 }
 
+// v5-only specialisations: L*P that is not a power of two (3- and 5-level pyramids)
+#define MSDA_FOR_EACH_V5_EXTRA_SPEC(X) \
+    X(32, 3, 4)                        \
+    X(64, 3, 4)                        \
+    X(32, 5, 4)                        \
+    X(64, 5, 4)
+
+template <int DD, int LL, int PP, int E>
+constexpr bool v5_ok()
+{
+    constexpr int LPT = DD / E, G = 32 / LPT, LP = LL * PP, PPG = LP / G;
+    return DD % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && PPG >= 1 && PPG <= LPT;
+}
+
 template <typename T>
 bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                    const void *attn, void *out, cudaStream_t st)
@@ -351,7 +365,7 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
     if (d->batch > 65535) return false;  // gridDim.y
     const bool w8 = g_warps.load() >= 8;
 #define X(DD, LL, PP)                                                                                  \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                            \
+    if constexpr (v5_ok<DD, LL, PP, E>()) {                                                            \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                   \
             w8 ? fwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, out, st)            \
                : fwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, out, st);           \
@@ -359,6 +373,7 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
         }                                                                                              \
     }
     MSDA_FOR_EACH_SPEC(X)
+    MSDA_FOR_EACH_V5_EXTRA_SPEC(X)
 #undef X
     return false;
 }
@@ -372,7 +387,7 @@ bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
     if (d->batch > 65535) return false;
     const bool w8 = g_warps.load() >= 8;
 #define X(DD, LL, PP)                                                                                             \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                       \
+    if constexpr (v5_ok<DD, LL, PP, E>()) {                                                                       \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                              \
             w8 ? bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,   \
                                                  gattn, st)                                                       \
@@ -382,6 +397,7 @@ bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
         }                                                                                                         \
     }
     MSDA_FOR_EACH_SPEC(X)
+    MSDA_FOR_EACH_V5_EXTRA_SPEC(X)
 #undef X
     return false;
 }

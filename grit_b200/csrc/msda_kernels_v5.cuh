@@ -170,7 +170,7 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     constexpr int LPT = D / E;
     constexpr int G = 32 / LPT;
     constexpr int LP = L * P;
-    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32, "unsupported");
 
     __shared__ int sH[L], sW[L], sStart[L];
     stage_levels<L>(shapes, lsi, sH, sW, sStart);
@@ -250,6 +250,33 @@ __device__ __forceinline__ void bwd_row_body(const ACC &accp, const Resolved &mi
     }
 }
 
+// Group-wide sums of the 3*PPG per-point scalars.  Power-of-two PPG: halving reduction (msda_kernels_v2.cuh), the
+// holder of iteration `it` is lane sub = it * (LPT/PPG).  Other PPG (L*P = 12, 20, ... as in 3- or 5-level pyramids):
+// plain butterflies, the holder of iteration `it` is lane sub = it.  Returns whether this lane is a holder; `it` and
+// r[0..2] are then its iteration and that iteration's (d/d attn, a*d/dw, a*d/dh).
+template <int PPG, int LPT>
+__device__ __forceinline__ bool reduce_points(float (&part)[3 * PPG], int sub, int &it, float (&r)[3])
+{
+    if constexpr ((PPG & (PPG - 1)) == 0) {
+        group_reduce3<PPG, LPT>(part, sub);
+        constexpr int SPAN = LPT / PPG;
+        it = sub / SPAN;
+        r[0] = part[0], r[1] = part[1], r[2] = part[2];
+        return (sub % SPAN) == 0;
+    } else {
+#pragma unroll
+        for (int width = LPT / 2; width >= 1; width >>= 1)
+#pragma unroll
+            for (int i = 0; i < 3 * PPG; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], width);
+        it = sub < PPG ? sub : 0;
+        r[0] = r[1] = r[2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < PPG; ++k)
+            if (k == it) r[0] = part[3 * k], r[1] = part[3 * k + 1], r[2] = part[3 * k + 2];
+        return sub < PPG;
+    }
+}
+
 template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))  // <= 64 registers: 32 resident warps per SM
 msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
@@ -262,8 +289,8 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     constexpr int G = 32 / LPT;
     constexpr int LP = L * P;
     constexpr int PPG = LP / G;
-    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
-    static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
+    static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32, "unsupported");
+    static_assert(PPG <= LPT, "one holder lane per point of the group is needed");
 
     __shared__ int sH[L], sW[L], sStart[L];
     stage_levels<L>(shapes, lsi, sH, sW, sStart);
@@ -295,14 +322,13 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     else
         bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part);
 
-    group_reduce3<PPG, LPT>(part, sub);
-    constexpr int SPAN = LPT / PPG;
-    if (sub % SPAN == 0) {
-        const int pt = (sub / SPAN) * G + g;
+    int it;
+    float r3[3];
+    if (reduce_points<PPG, LPT>(part, sub, it, r3)) {
+        const int pt = it * G + g;
         const int l = pt / P;
-        reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] =
-            make_float2((float)sW[l] * part[1], (float)sH[l] * part[2]);
-        grad_attn[row * LP + pt] = part[0];
+        reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] = make_float2((float)sW[l] * r3[1], (float)sH[l] * r3[2]);
+        grad_attn[row * LP + pt] = r3[0];
     }
 }
 

@@ -118,7 +118,11 @@ RANDOM_CASES = [
     (2, 29, 8, 32, [(9, 14)], 4, True),
     (2, 17, 3, 5, [(5, 7), (1, 1), (2, 3)], 2, False),
     (1, 9, 2, 71, [(4, 4), (2, 2)], 3, False),
-    (3, 5, 8, 32, [(7, 9), (4, 5), (2, 3)], 4, False),
+    (3, 5, 8, 32, [(7, 9), (4, 5), (2, 3)], 4, True),                      # L*P = 12 (3-level pyramid)
+    (2, 31, 8, 64, [(7, 9), (4, 5), (2, 3)], 4, True),
+    (2, 27, 8, 32, [(11, 13), (7, 9), (4, 5), (2, 3), (1, 2)], 4, True),   # L*P = 20 (5-level pyramid)
+    (1, 14, 4, 64, [(11, 13), (7, 9), (4, 5), (2, 3), (1, 2)], 4, True),
+    (2, 9, 8, 32, [(7, 9), (4, 5), (2, 3)], 2, False),                     # L*P = 6: no specialisation
     (1, 6, 1, 40, [(3, 1), (1, 5)], 1, False),
 ]
 
