@@ -300,12 +300,17 @@ void fwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes,
 {
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
-    const bool hoist = g_hoist.load() != 0;
-    if (hoist)
-        msda::msda_fwd_v5<T, DD, LL, PP, W, true><<<grid, W * 32, 0, st>>>(
-            (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
-            (int)d->num_heads, rpi);
-    else
+    constexpr bool kFlagship = DD == 32 && LL == 4 && PP == 4;  // the A/B variants exist for this shape only
+    bool hoist = false;
+    if constexpr (kFlagship) hoist = g_hoist.load() != 0;
+    if constexpr (kFlagship) {
+        if (hoist) {
+            msda::msda_fwd_v5<T, DD, LL, PP, W, true><<<grid, W * 32, 0, st>>>(
+                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out,
+                (int)d->spatial_size, (int)d->num_heads, rpi);
+        }
+    }
+    if (!hoist)
         msda::msda_fwd_v5<T, DD, LL, PP, W, false><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
             (int)d->num_heads, rpi);
@@ -367,8 +372,13 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
 #define X(DD, LL, PP)                                                                                  \
     if constexpr (v5_ok<DD, LL, PP, E>()) {                                                            \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                   \
-            w8 ? fwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, out, st)            \
-               : fwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, out, st);           \
+            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                      \
+                if (w8) {                                                                              \
+                    fwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, out, st);        \
+                    return true;                                                                       \
+                }                                                                                      \
+            }                                                                                          \
+            fwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, out, st);                \
             return true;                                                                               \
         }                                                                                              \
     }
@@ -389,10 +399,15 @@ bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
 #define X(DD, LL, PP)                                                                                             \
     if constexpr (v5_ok<DD, LL, PP, E>()) {                                                                       \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                              \
-            w8 ? bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,   \
-                                                 gattn, st)                                                       \
-               : bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,   \
-                                                 gattn, st);                                                      \
+            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                                 \
+                if (w8) {                                                                                         \
+                    bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale,    \
+                                                    gloc, gattn, st);                                             \
+                    return true;                                                                                  \
+                }                                                                                                 \
+            }                                                                                                     \
+            bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,      \
+                                            gattn, st);                                                           \
             return true;                                                                                          \
         }                                                                                                         \
     }
