@@ -138,6 +138,7 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     typename ACC::elem *gimg = gv_acc + img;
     ACC accp;
     if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
+    accp.template prepare<T, E>(grad_out + row * D, sub, LPT);
 
     const int rp = lane % LP;
     const int rl = rp / P;

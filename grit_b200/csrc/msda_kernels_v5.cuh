@@ -45,6 +45,10 @@ __device__ __forceinline__ void red_chunk(float *p, const float (&g)[E], float s
 //           sum up to 2^-k).  Costs 8-byte scalar reds instead of 16-byte vector ones.
 struct AccF32 {
     using elem = float;
+    template <typename T, int E>
+    __device__ __forceinline__ void prepare(const T *, int, int)
+    {
+    }
     template <int E, bool ALL>
     __device__ __forceinline__ void add(float *p, const float (&g)[E], float s, int pred) const
     {
@@ -52,17 +56,30 @@ struct AccF32 {
     }
 };
 
+// The 8-byte integer reds have no vector form, so the lane -> channel map is re-cut for them: lane `sub` owns channels
+// sub, sub+LPT, sub+2*LPT, ... (instead of E consecutive ones), which makes the LPT lanes of a tap hit LPT consecutive
+// 8-byte words per instruction -- whole 32-byte sectors -- instead of one word in each of LPT different sectors.
 struct AccFix64 {
     using elem = unsigned long long;
-    float scale;  // 2^k
+    float scale;       // 2^k
+    float gs[8];       // this lane's grad_out values in the strided channel map
+    int sub, sub_e, lpt;
+    template <typename T, int E>
+    __device__ __forceinline__ void prepare(const T *grad_row, int sub_, int lpt_)
+    {
+        sub = sub_, lpt = lpt_, sub_e = sub_ * E;
+#pragma unroll
+        for (int e = 0; e < E; ++e) gs[e] = to_c<float, T>(grad_row[sub_ + lpt_ * e]);
+    }
     template <int E, bool ALL>
-    __device__ __forceinline__ void add(unsigned long long *p, const float (&g)[E], float s, int pred) const
+    __device__ __forceinline__ void add(unsigned long long *p, const float (&)[E], float s, int pred) const
     {
         if (ALL || pred) {
+            unsigned long long *line = p - sub_e + sub;  // first word of this lane in the tap's line
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const long long q = __float2ll_rn(s * g[e] * scale);
-                if (q != 0) atomicAdd(p + e, (unsigned long long)q);
+                const long long q = __float2ll_rn(s * gs[e] * scale);
+                if (q != 0) atomicAdd(line + lpt * e, (unsigned long long)q);
             }
         }
     }
@@ -307,6 +324,7 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     typename ACC::elem *gimg = gv_acc + img;
     ACC accp;
     if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
+    accp.template prepare<T, E>(grad_out + row * D, sub, LPT);
 
     const int rp = lane % LP;
     const int rl = rp / P;
