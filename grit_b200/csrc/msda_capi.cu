@@ -1163,7 +1163,8 @@ int msda_host_session_create(msda_host_session **session, const msda_dims *max_d
     const size_t n_out = c * d.num_query * d.num_heads * d.channels;
     msda_dims cd = d;
     cd.batch = images_per_chunk;
-    s->ws_bytes = msda_backward_workspace_bytes(&cd, dtype, 0);
+    // sized for the most demanding mode (deterministic) so any flags accepted by msda_backward work through a session
+    s->ws_bytes = msda_backward_workspace_bytes(&cd, dtype, dtype == MSDA_F64 ? 0 : MSDA_FLAG_DETERMINISTIC);
     cudaError_t e = cudaSuccess;
     auto alloc = [&](char **p, size_t bytes) {
         if (e == cudaSuccess) e = cudaMalloc((void **)p, bytes ? bytes : 16);

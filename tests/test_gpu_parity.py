@@ -679,6 +679,9 @@ def test_host_session_matches_device_path(lib, oracle):
     dims = lib.MsdaDims(5, value.shape[1], 8, 32, 4, 33, 4)
     sess = lib.HostSession(dims, torch.float32, device=0, images_per_chunk=2)
     sess.forward_backward(value, shapes, lsi, loc, attn, gout, out, gv, gl, ga)
+    gv_float = gv.clone()
+    sess.forward_backward(value, shapes, lsi, loc, attn, gout, out, gv, gl, ga, flags=lib.FLAG_DETERMINISTIC)
+    assert max_norm_err(gv.numpy(), gv_float.numpy()) < 1e-5  # deterministic mode through the same session
     sess.close()
     ref = oracle_results(oracle, case)
     assert max_norm_err(out.numpy(), ref["out"]) < 1e-5
