@@ -173,6 +173,25 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_warned_generic = set()
+
+
+def _warn_if_generic(lib, value, dims):
+    """One warning per (D, L, P, dtype) when a large fp32/bf16 problem lands on the scalar generic kernels (the
+    reference warns similarly about non-power-of-two head widths, modules/ms_deform_attn.py:37-40)."""
+    if value.dtype == torch.float64 or dims.batch * dims.num_query * dims.num_heads < 100_000:
+        return
+    key = (dims.channels, dims.num_levels, dims.num_point, value.dtype)
+    if key in _warned_generic or not lib.msda_last_kernel().startswith(b"fwd_generic"):
+        return
+    _warned_generic.add(key)
+    import warnings
+    warnings.warn(f"grit_b200: no specialised kernel for D={dims.channels}, L={dims.num_levels}, P={dims.num_point}, "
+                  f"{value.dtype} (or the tensors are not 16-byte aligned); using the generic path, which is several "
+                  "times slower.  Specialised: D in {16,32,64,128} with (L,P) in {(4,4),(4,8),(1,4),(1,8)}, "
+                  "D in {32,64} with (L,P) in {(3,4),(5,4)}.")
+
+
 def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, flags: int = 0):
     """-> output (N, Lq, M*D).  Mirrors ms_deform_attn_cuda_forward (ms_deform_attn_cuda.cu:20-80)."""
     lib = load()
@@ -186,6 +205,7 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                               ctypes.c_void_p(stream))
     if rc:
         _raise(lib, rc, "msda_forward")
+    _warn_if_generic(lib, value, dims)
     return out
 
 
