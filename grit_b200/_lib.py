@@ -205,7 +205,8 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
                               ctypes.c_void_p(stream))
     if rc:
         _raise(lib, rc, "msda_forward")
-    _warn_if_generic(lib, value, dims)
+    if not flags & FLAG_FORCE_GENERIC:
+        _warn_if_generic(lib, value, dims)
     return out
 
 
