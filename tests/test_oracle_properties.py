@@ -18,7 +18,7 @@ geometry = st.tuples(
 )
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(geometry)
 def test_c_and_numpy_restatements_agree(oracle, geo):
     N, Lq, M, D, shapes, P, seed = geo
@@ -30,7 +30,7 @@ def test_c_and_numpy_restatements_agree(oracle, geo):
         assert np.abs(out_c - out_np).max() <= 1e-12 * max(1.0, np.abs(out_np).max())
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(geometry)
 def test_adjoint_identities_hold_for_the_oracle(oracle, geo):
     """<out, g> == <value, grad_value> == <attn, grad_attn>: the forward is linear in value and in attn."""
@@ -45,7 +45,7 @@ def test_adjoint_identities_hold_for_the_oracle(oracle, geo):
     assert abs(lhs - float((case["attn"] * ga).sum())) <= 1e-10 * scale + 1e-12
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(geometry)
 def test_location_gradient_matches_finite_differences(oracle, geo):
     N, Lq, M, D, shapes, P, seed = geo
