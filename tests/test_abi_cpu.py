@@ -35,7 +35,8 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_library_contains_sm100a_code(lib):
-    out = os.popen(f"cuobjdump -lelf {build.LIB_PATH} 2>/dev/null").read()
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", build.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
 
 
