@@ -45,6 +45,11 @@ WORKLOADS = {
                                       dtype="f32", layers=6),
     "grit_decoder_800x1333_bf16": dict(N=32, shapes=[(100, 167), (50, 84), (25, 42), (13, 21)], Lq=150, M=8, D=64, P=4,
                                        dtype="bf16", layers=6),
+    # GRIT's real operating point: no AMP, C=512 / D=64, 150 queries (det_module.py:285,335-336; train_config.yaml:34-41)
+    "grit_decoder_384x640_f32": dict(N=64, shapes=[(48, 80), (24, 40), (12, 20), (6, 10)], Lq=150, M=8, D=64, P=4,
+                                     dtype="f32", layers=6),
+    "grit_decoder_800x1333_f32": dict(N=32, shapes=[(100, 167), (50, 84), (25, 42), (13, 21)], Lq=150, M=8, D=64, P=4,
+                                      dtype="f32", layers=6),
     "tiny": dict(N=2, shapes=[(12, 20), (6, 10), (3, 5), (2, 3)], Lq=None, M=8, D=32, P=4, dtype="f32", layers=2),
 }
 OP_PARAMS_PER_LAYER = {256: 230272, 512: 722304}  # the four Linears of one MSDeformAttn
@@ -181,9 +186,39 @@ def make_layer_inputs(torch, cfg, device, seed, loc_dist):
     return dict(value=value.contiguous(), loc=loc.contiguous(), attn=attn.contiguous(), gout=gout.contiguous())
 
 
+def load_reference_core():
+    """The reference's own ``ms_deform_attn_core_pytorch`` (models/ops/functions/ms_deform_attn_func.py:41-61), loaded
+    UNMODIFIED from the copy __graft_entry__.build() leaves in git-ignored baseline/_ref/ops_test.  The file imports the
+    compiled extension at module top (:18); the CPU function never calls it, so an empty stand-in module satisfies the
+    import.  Returns None when the copy is absent (then the restated port in oracle/msda_ref_torch.py is timed)."""
+    path = os.path.join(ROOT, "baseline", "_ref", "ops_test", "functions", "ms_deform_attn_func.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    import types
+    name = "MultiScaleDeformableAttention"
+    prev = sys.modules.get(name)
+    sys.modules[name] = types.ModuleType(name)
+    try:
+        spec = importlib.util.spec_from_file_location("_grit_reference_ms_deform_attn_func", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.ms_deform_attn_core_pytorch
+    except Exception:
+        return None
+    finally:
+        if prev is None:
+            sys.modules.pop(name, None)
+        else:
+            sys.modules[name] = prev
+
+
 def cpu_reference_pass(torch, cfg, images, threads, steps, warmup, loc_dist):
-    """The reference's CPU path (grid_sample composition) fwd + autograd bwd on `images` images per step."""
+    """The reference's CPU path (grid_sample composition) fwd + autograd bwd on `images` images per step.
+    Returns (queries/s, s/step, sample description, kind): kind "reference" = the reference's own function,
+    "port" = the restatement in oracle/msda_ref_torch.py."""
     from oracle import msda_ref_torch
+    ref_core = load_reference_core()
     torch.set_num_threads(threads)
     small = dict(cfg, N=images)
     data = make_layer_inputs(torch, dict(small, dtype="f32"), "cpu", 0, loc_dist)
@@ -193,13 +228,21 @@ def cpu_reference_pass(torch, cfg, images, threads, steps, warmup, loc_dist):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        msda_ref_torch.forward_backward(data["value"], shapes, data["loc"], data["attn"], data["gout"])
+        if ref_core is not None:
+            v = data["value"].detach().requires_grad_(True)
+            lo = data["loc"].detach().requires_grad_(True)
+            at = data["attn"].detach().requires_grad_(True)
+            ref_core(v, shapes, lo, at).backward(data["gout"])
+        else:
+            msda_ref_torch.forward_backward(data["value"], shapes, data["loc"], data["attn"], data["gout"])
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
+    what = "the reference's own ms_deform_attn_core_pytorch" if ref_core is not None else "oracle/msda_ref_torch.py port"
     return images * Lq * len(times) / total, total / len(times), f"{images} image(s) of the workload shape per step, " \
-        f"1 layer fwd+autograd bwd, fp32, {len(times)} timed steps after {warmup} warm-up, torch {torch.__version__} CPU"
+        f"1 layer fwd+autograd bwd ({what}), fp32, {len(times)} timed steps after {warmup} warm-up, " \
+        f"torch {torch.__version__} CPU", ("reference" if ref_core is not None else "port")
 
 
 def run_reference_arm(args, cfg, rank):
@@ -209,13 +252,13 @@ def run_reference_arm(args, cfg, rank):
     threads = os.cpu_count() or 1
     S = sum(h * w for h, w in cfg["shapes"])
     Lq = cfg["Lq"] or S
-    qps, sec_per_step, sample = cpu_reference_pass(torch, cfg, 2, threads, args.steps, args.warmup, args.loc_dist)
+    qps, sec_per_step, sample, kind = cpu_reference_pass(torch, cfg, 2, threads, args.steps, args.warmup, args.loc_dist)
     line = {
         "impl": "reference", "metric": "msda_fwd_bwd_queries_per_sec", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg, args.gpus),
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -573,8 +616,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, _, sample = cpu_reference_pass(torch, cfg, 2, threads, 16, 1, args.loc_dist)  # ~10 s of CPU work
-        cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample}
+        v, _, sample, kind = cpu_reference_pass(torch, cfg, 2, threads, 16, 1, args.loc_dist)  # ~10 s of CPU work
+        cpu = {"value": v, "unit": "queries/s", "cores": threads, "kind": kind, "sample": sample}
 
     if rank == 0:
         line = {

@@ -18,6 +18,7 @@ MSDA_F32, MSDA_F64, MSDA_BF16 = 0, 1, 2
 FLAG_ZERO_GRAD_VALUE = 1 << 0
 FLAG_DETERMINISTIC = 1 << 1
 FLAG_FORCE_GENERIC = 1 << 2
+FLAG_ALIGNED16 = 1 << 3  # msda_backward_workspace_bytes only: every tensor of the coming call is 16-byte aligned
 
 _DTYPE_CODE = {torch.float32: MSDA_F32, torch.float64: MSDA_F64, torch.bfloat16: MSDA_BF16}
 
@@ -106,6 +107,10 @@ def load():
         lib.msda_host_forward_backward.restype = ctypes.c_int
         lib.msda_host_forward_backward.argtypes = [vp, vp, i64p, i64p, vp, vp, vp, vp, vp, vp, vp, dimsp,
                                                    ctypes.c_uint]
+        lib.msda_host_submit.restype = ctypes.c_int
+        lib.msda_host_submit.argtypes = lib.msda_host_forward_backward.argtypes
+        lib.msda_host_wait.restype = ctypes.c_int
+        lib.msda_host_wait.argtypes = [vp]
         if lib.msda_abi_version() != 1:
             raise RuntimeError(f"{path}: ABI version {lib.msda_abi_version()} != 1")
         _lib = lib
@@ -121,7 +126,8 @@ def launch_count(reset: bool = False) -> int:
 
 
 def set_tuning(key: str, value: int) -> int:
-    """A/B knob of the library (include/msda.h: msda_set_tuning); returns the previous value."""
+    """A/B knob of the library (include/msda.h: msda_set_tuning: "variant", "hoist", "warps", "v3_threads",
+    "bwd_mode", "bin_min_rows", "owned_max_taps"); returns the previous value."""
     prev = load().msda_set_tuning(key.encode(), int(value))
     if prev < 0:
         raise KeyError(key)
@@ -217,12 +223,13 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     code = _DTYPE_CODE[value.dtype]
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
-    ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags)
-    if ws_bytes:  # bf16 and/or deterministic: accumulation happens in the workspace, a fold kernel writes grad_value
-        grad_value = torch.empty_like(value)
-        flags |= FLAG_ZERO_GRAD_VALUE  # the fold kernel then overwrites instead of accumulating
-    else:
-        grad_value = torch.zeros_like(value)
+    # grad_value is allocated uninitialised: with FLAG_ZERO_GRAD_VALUE the library zero-fills it on the stream when its
+    # strategy accumulates into it (row kernels), overwrites it from the workspace (bf16 / deterministic fold) or writes
+    # every line exactly once (owned backward: no fill at all)
+    grad_value = torch.empty_like(value)
+    flags |= FLAG_ZERO_GRAD_VALUE
+    aligned = all(t.data_ptr() % 16 == 0 for t in (value, sampling_loc, attn_weight, grad_output, grad_value, grad_loc))
+    ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags | (FLAG_ALIGNED16 if aligned else 0))
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device), _nvtx_range("msda_backward"):
         stream = torch.cuda.current_stream().cuda_stream
@@ -291,11 +298,62 @@ def fused_dims(value, sampling_offsets, reference_points):
     return MsdaDims(n, s, m, d, l, lq, p)
 
 
-def fused_supported(value, sampling_offsets, reference_points) -> bool:
-    """True when the fused kernels (include/msda.h: msda_fused_*) cover this problem."""
-    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16):
-        return False
-    if sampling_offsets.dtype != torch.float32 or reference_points.dtype != torch.float32:
+def _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                   padding_mask=None, grad_output=None):
+    """Why the fused kernels cannot take these tensors (a string), or None when they can.  The fused entry points do
+    raw pointer arithmetic on every argument, so shapes, dtypes, devices, contiguity and alignment are all checked
+    here -- the same role _check_inputs plays for msda_forward/backward."""
+    if not value.is_cuda:
+        return "Not implemented on the CPU"
+    if value.dtype not in (torch.float32, torch.bfloat16):
+        return f"fused kernels take fp32 / bf16 values, got {value.dtype}"
+    if value.dim() != 4 or sampling_offsets.dim() != 6 or sampling_offsets.shape[-1] != 2:
+        return "expected value (N,S,M,D) and sampling_offsets (N,Lq,M,L,P,2)"
+    n, s, m, d = value.shape
+    n2, lq, m2, l, p, _ = sampling_offsets.shape
+    if (n2, m2) != (n, m):
+        return "value / sampling_offsets shapes disagree"
+    if tuple(attn_logits.shape) != (n, lq, m, l * p):
+        return f"attn_logits must be (N,Lq,M,L*P) = {(n, lq, m, l * p)}, got {tuple(attn_logits.shape)}"
+    if reference_points.dim() != 4 or tuple(reference_points.shape[:3]) != (n, lq, l) or \
+            reference_points.shape[-1] not in (2, 4):
+        return f"reference_points must be (N,Lq,L,2|4) = {(n, lq, l)} + (2|4,), got {tuple(reference_points.shape)}"
+    for name, t in (("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+                    ("reference_points", reference_points)):
+        if t.dtype != torch.float32:
+            return f"{name} must be float32, got {t.dtype}"
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        return "spatial_shapes and level_start_index must be int64 (torch.long) tensors"
+    if tuple(spatial_shapes.shape) != (l, 2) or level_start_index.numel() != l:
+        return "spatial_shapes must be (L,2) and level_start_index (L,)"
+    named = [("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+             ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
+             ("level_start_index", level_start_index)]
+    if grad_output is not None:
+        if grad_output.dtype != value.dtype or grad_output.numel() != n * lq * m * d:
+            return "grad_output must have value's dtype and N*Lq*M*D elements"
+        named.append(("grad_output", grad_output))
+    if padding_mask is not None:
+        if padding_mask.dtype != torch.bool or tuple(padding_mask.shape) != (n, s):
+            return f"padding_mask must be a bool (N,S) = {(n, s)} tensor"
+        named.append(("padding_mask", padding_mask))
+    for name, t in named:
+        if t.device != value.device:
+            return f"{name} is on {t.device}, value is on {value.device}"
+        if not t.is_contiguous():
+            return f"{name} tensor has to be contiguous"
+    for name, t in named[:4] + named[6:7]:
+        if t.data_ptr() % 16:
+            return f"{name} storage is not 16-byte aligned"
+    return None
+
+
+def fused_supported(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                    padding_mask=None) -> bool:
+    """True when the fused kernels (include/msda.h: msda_fused_*) cover this problem AND the tensors are laid out the
+    way the kernels index them; the module falls back to the validated reference-shaped path otherwise."""
+    if _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                      padding_mask) is not None:
         return False
     dims = fused_dims(value, sampling_offsets, reference_points)
     return bool(load().msda_fused_supported(ctypes.byref(dims), _DTYPE_CODE[value.dtype],
@@ -307,8 +365,10 @@ def mask_rows_(data, mask):
     lib = load()
     row_bytes = data.shape[-1] * data.element_size() if mask.dim() == data.dim() - 1 else \
         data[(0,) * mask.dim()].numel() * data.element_size()
-    if not (data.is_contiguous() and mask.is_contiguous() and mask.dtype == torch.bool):
-        raise RuntimeError("mask_rows_ expects contiguous data and a contiguous bool mask")
+    if not (data.is_cuda and data.is_contiguous() and mask.is_contiguous() and mask.dtype == torch.bool and
+            mask.device == data.device and tuple(data.shape[:mask.dim()]) == tuple(mask.shape)):
+        raise RuntimeError("mask_rows_ expects contiguous CUDA data (..., R) and a contiguous bool mask (...) on the "
+                           "same device")
     with torch.cuda.device(data.device):
         rc = lib.msda_mask_rows(_ptr(data), _ptr(mask), mask.numel(), row_bytes,
                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
@@ -319,13 +379,9 @@ def mask_rows_(data, mask):
 
 def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
     lib = load()
-    for name, t in (("value", value), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
-                    ("reference_points", reference_points), ("spatial_shapes", spatial_shapes),
-                    ("level_start_index", level_start_index)):
-        if not t.is_contiguous():
-            raise RuntimeError(f"{name} tensor has to be contiguous")
-        if not t.is_cuda:
-            raise RuntimeError(f"{name} must be a CUDA tensor")
+    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)
+    if why:
+        raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
@@ -342,6 +398,10 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
 def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
                    grad_output, flags: int = 0):
     lib = load()
+    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                         grad_output=grad_output)
+    if why:
+        raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
     code = _DTYPE_CODE[value.dtype]
     grad_offs = torch.empty_like(sampling_offsets)
@@ -377,22 +437,40 @@ class HostSession:
         if rc:
             _raise(self._lib, rc, "msda_host_session_create")
 
-    def forward_backward(self, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                         output, grad_value, grad_loc, grad_attn, flags: int = 0):
-        """All arguments are HOST tensors (ideally pinned); outputs are written in place."""
+    def _call(self, fn, name, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+              output, grad_value, grad_loc, grad_attn, flags):
         for t in (value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output, output,
                   grad_value, grad_loc, grad_attn):
             if t.is_cuda or not t.is_contiguous():
                 raise RuntimeError("HostSession expects contiguous host tensors")
+        if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+            raise RuntimeError("spatial_shapes and level_start_index must be int64 (torch.long) tensors")
         n, s, m, d = value.shape
         _, lq, _, l, p, _ = sampling_loc.shape
         dims = MsdaDims(n, s, m, d, l, lq, p)
-        rc = self._lib.msda_host_forward_backward(
-            self._handle, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
-            _ptr(attn_weight), _ptr(grad_output), _ptr(output), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
-            ctypes.byref(dims), flags)
+        rc = fn(self._handle, _ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+                _ptr(attn_weight), _ptr(grad_output), _ptr(output), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
+                ctypes.byref(dims), flags)
         if rc:
-            _raise(self._lib, rc, "msda_host_forward_backward")
+            _raise(self._lib, rc, name)
+
+    def forward_backward(self, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                         output, grad_value, grad_loc, grad_attn, flags: int = 0):
+        """All arguments are HOST tensors (ideally pinned); outputs are written in place; returns when they have landed."""
+        self._call(self._lib.msda_host_forward_backward, "msda_host_forward_backward", value, spatial_shapes,
+                   level_start_index, sampling_loc, attn_weight, grad_output, output, grad_value, grad_loc, grad_attn,
+                   flags)
+
+    def submit(self, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+               output, grad_value, grad_loc, grad_attn, flags: int = 0):
+        """Enqueue one forward+backward and return at once (msda_host_submit); call wait() before touching the buffers."""
+        self._call(self._lib.msda_host_submit, "msda_host_submit", value, spatial_shapes, level_start_index,
+                   sampling_loc, attn_weight, grad_output, output, grad_value, grad_loc, grad_attn, flags)
+
+    def wait(self):
+        rc = self._lib.msda_host_wait(self._handle)
+        if rc:
+            _raise(self._lib, rc, "msda_host_wait")
 
     def close(self):
         if self._handle:

@@ -11,8 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "msda_kernels_v3.cuh"
 #include "msda_kernels_fused.cuh"
+#include "msda_kernels_staged.cuh"
 
 #include <atomic>
 #include <type_traits>
@@ -62,6 +62,8 @@ int check_dims(const msda_dims *d, int dtype)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "per-image size overflows");
     if (d->batch * d->num_query * d->num_heads > ((int64_t)1 << 40))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "batch*num_query*num_heads too large");
+    if (d->spatial_size >= ((int64_t)1 << 31) || d->num_query >= ((int64_t)1 << 31) || d->batch >= ((int64_t)1 << 31))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "batch, num_query and spatial_size must be below 2^31");
     return MSDA_OK;
 }
 
@@ -69,12 +71,15 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 constexpr int kWarps = 8;
 
-// Process-wide tuning knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/).
-std::atomic<int> g_variant{5};     // 1 | 2 | 3 | 4 | 5 select a kernel generation (5 = measured best); 0 = auto by size
-std::atomic<int> g_v3_threads{1024};  // v3 CTA size: 512 or 1024
-std::atomic<int> g_v3_min_rows{256};  // auto mode: v3 when M*Lq / #SMs >= this
-std::atomic<int> g_head_major{0};  // v2 only: 0 = rows in memory order (b,q,m), 1 = (b,m,q)
-std::atomic<int> g_warps{4};       // v2 warps per CTA for the flagship specialisation: 4, 8 or 16
+// Process-wide A/B knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/); they exist for
+// benchmarking and tests, results do not depend on them beyond fp rounding.
+std::atomic<int> g_variant{5};        // forward: 5 = lean row kernel (default) | 3 = persistent shared-memory-staged
+std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 1024
+std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
+std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
+std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
+std::atomic<int> g_bin_min_rows{1024};   // auto: binned coarse levels when num_query >= this
+std::atomic<int> g_owned_max_taps{4};    // auto: owned when taps per value pixel (Lq*L*P*4 / S) <= this
 
 struct Geometry {
     int64_t rows;
@@ -97,7 +102,26 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
     if (d->batch * d->num_query * d->num_heads >= ((int64_t)1 << 31)) return false;  // 32-bit row index
     if (d->num_heads * d->num_query >= ((int64_t)1 << 31)) return false;
     if (d->spatial_size >= ((int64_t)1 << 27)) return false;  // pixel index is packed as pix*16 + tap mask
+    if (d->batch > 65535) return false;                        // gridDim.y
     return d->spatial_size * d->num_heads * d->channels < ((int64_t)1 << 31);
+}
+
+struct DeviceInfo {
+    int sms = 0;
+    int max_smem_optin = 0;
+};
+
+const DeviceInfo &device_info()
+{
+    thread_local DeviceInfo cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceInfo &d = cache[dev & 63];
+    if (d.sms == 0) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    return d;
 }
 
 // ---- specialisation tables -----------------------------------------------------------------------
@@ -111,11 +135,15 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
     X(32, 1, 4)               \
     X(64, 1, 4)               \
     X(32, 1, 8)               \
-    X(64, 1, 8)
+    X(64, 1, 8)               \
+    X(32, 3, 4)               \
+    X(64, 3, 4)               \
+    X(32, 5, 4)               \
+    X(64, 5, 4)
 
-// first-generation kernels are kept for A/B only: flagship shapes
-#define MSDA_FOR_EACH_V1_SPEC(X) \
-    X(32, 4, 4)                  \
+// shapes with the staged forward, the binned / owned backward and the fused module kernels
+#define MSDA_FOR_EACH_FLAGSHIP_SPEC(X) \
+    X(32, 4, 4)                        \
     X(64, 4, 4)
 
 template <typename T>
@@ -125,182 +153,14 @@ const char *tname<float>() { return "f32"; }
 template <>
 const char *tname<__nv_bfloat16>() { return "bf16"; }
 
-template <typename T>
-bool launch_fwd_vec(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
-                    const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st)
-{
-    constexpr int E = msda::Chunk<T>::E;
-#define X(DD, LL, PP)                                                                                          \
-    if constexpr ((DD) % E == 0 && 32 % ((DD) / E) == 0 && ((LL) * (PP)) % (32 / ((DD) / E)) == 0) {          \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                           \
-            msda::msda_fwd_vec<T, DD, LL, PP, kWarps><<<g.grid, kWarps * 32, 0, st>>>(                        \
-                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out,             \
-                (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, g.rows);                          \
-            snprintf(tl_kernel, sizeof(tl_kernel), "fwd_vec<%s,D%d,L%d,P%d>", tname<T>(), DD, LL, PP);        \
-            return true;                                                                                       \
-        }                                                                                                      \
-    }
-    MSDA_FOR_EACH_V1_SPEC(X)
-#undef X
-    return false;
-}
-
-template <typename T>
-bool launch_bwd_vec(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
-                    const int64_t *lsi, const void *loc, const void *attn, const void *gout, float *gv_acc,
-                    void *gloc, void *gattn, cudaStream_t st)
-{
-    constexpr int E = msda::Chunk<T>::E;
-#define X(DD, LL, PP)                                                                                          \
-    if constexpr ((DD) % E == 0 && 32 % ((DD) / E) == 0 && ((LL) * (PP)) % (32 / ((DD) / E)) == 0 &&          \
-                  ((LL) * (PP)) / (32 / ((DD) / E)) <= (DD) / E) {                                             \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                           \
-            msda::msda_bwd_vec<T, DD, LL, PP, kWarps><<<g.grid, kWarps * 32, 0, st>>>(                        \
-                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout,      \
-                gv_acc, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads,               \
-                (int)d->num_query, g.rows);                                                                    \
-            snprintf(tl_kernel, sizeof(tl_kernel), "bwd_vec<%s,D%d,L%d,P%d>", tname<T>(), DD, LL, PP);        \
-            return true;                                                                                       \
-        }                                                                                                      \
-    }
-    MSDA_FOR_EACH_V1_SPEC(X)
-#undef X
-    return false;
-}
-
-template <typename T, int DD, int LL, int PP, int W, bool HM>
-void fwd_v2_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
-                   const void *loc, const void *attn, void *out, cudaStream_t st)
-{
-    const unsigned grid = (unsigned)((rows + W - 1) / W);
-    msda::msda_fwd_v2<T, DD, LL, PP, W, HM><<<grid, W * 32, 0, st>>>(
-        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
-        (int)d->num_heads, (int)d->num_query, rows);
-    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v2<%s,D%d,L%d,P%d,w%d,%s>", tname<T>(), DD, LL, PP, W,
-             HM ? "head-major" : "row-major");
-}
-
-template <typename T, int DD, int LL, int PP, int W, bool HM>
-void bwd_v2_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
-                   const void *loc, const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn,
-                   cudaStream_t st)
-{
-    const unsigned grid = (unsigned)((rows + W - 1) / W);
-    msda::msda_bwd_v2<T, DD, LL, PP, W, HM><<<grid, W * 32, 0, st>>>(
-        (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, gv_acc,
-        (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rows);
-    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v2<%s,D%d,L%d,P%d,w%d,%s>", tname<T>(), DD, LL, PP, W,
-             HM ? "head-major" : "row-major");
-}
-
-template <typename T, int DD, int LL, int PP, int W>
-int fwd_v2p_launch(const msda_dims *d, int64_t rows, const void *value, const int64_t *shapes, const int64_t *lsi,
-                   const void *loc, const void *attn, void *out, cudaStream_t st)
-{
-    auto kernel = msda::msda_fwd_v2p<T, DD, LL, PP, W>;
-    thread_local int blocks_per_sm = 0;
-    thread_local int sms = 0;
-    if (blocks_per_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, W * 32, 0) != cudaSuccess ||
-            blocks_per_sm < 1)
-            blocks_per_sm = 1;
-    }
-    int64_t grid = (int64_t)sms * blocks_per_sm;
-    const int64_t need = (rows + W - 1) / W;
-    if (grid > need) grid = need;
-    kernel<<<(unsigned)grid, W * 32, 0, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
-                                              (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query,
-                                              rows);
-    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v2p<%s,D%d,L%d,P%d,w%d,persistent x%d>", tname<T>(), DD, LL, PP, W,
-             blocks_per_sm);
-    return MSDA_OK;
-}
-
-template <int DD, int LL, int PP, int E>
-constexpr bool v2_ok()
-{
-    constexpr int LPT = DD / E, G = 32 / LPT, LP = LL * PP, PPG = LP / G;
-    return DD % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0 && PPG >= 1 && PPG <= LPT &&
-           (PPG & (PPG - 1)) == 0;
-}
-
-template <typename T>
-bool launch_fwd_v2(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
-                   const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st)
-{
-    constexpr int E = msda::Chunk<T>::E;
-    const bool hm = g_head_major.load() != 0;
-    const int w = g_warps.load();
-#define X(DD, LL, PP)                                                                                        \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                  \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                         \
-            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                            \
-                if (w == 4) {                                                                                \
-                    hm ? fwd_v2_launch<T, DD, LL, PP, 4, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)   \
-                       : fwd_v2_launch<T, DD, LL, PP, 4, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st); \
-                    return true;                                                                             \
-                }                                                                                            \
-                if (w == 16) {                                                                               \
-                    hm ? fwd_v2_launch<T, DD, LL, PP, 16, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)  \
-                       : fwd_v2_launch<T, DD, LL, PP, 16, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st);\
-                    return true;                                                                             \
-                }                                                                                            \
-            }                                                                                                \
-            hm ? fwd_v2_launch<T, DD, LL, PP, 8, true>(d, g.rows, value, shapes, lsi, loc, attn, out, st)    \
-               : fwd_v2_launch<T, DD, LL, PP, 8, false>(d, g.rows, value, shapes, lsi, loc, attn, out, st);  \
-            return true;                                                                                     \
-        }                                                                                                    \
-    }
-    MSDA_FOR_EACH_SPEC(X)
-#undef X
-    return false;
-}
-
-template <typename T>
-bool launch_bwd_v2(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
-                   const int64_t *lsi, const void *loc, const void *attn, const void *gout, float *gv_acc,
-                   void *gloc, void *gattn, cudaStream_t st)
-{
-    constexpr int E = msda::Chunk<T>::E;
-    const bool hm = g_head_major.load() != 0;
-    const int w = g_warps.load();
-#define ARGS d, g.rows, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st
-#define X(DD, LL, PP)                                                                                        \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                  \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                         \
-            if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                            \
-                if (w == 4) {                                                                                \
-                    hm ? bwd_v2_launch<T, DD, LL, PP, 4, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 4, false>(ARGS);  \
-                    return true;                                                                             \
-                }                                                                                            \
-                if (w == 16) {                                                                               \
-                    hm ? bwd_v2_launch<T, DD, LL, PP, 16, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 16, false>(ARGS);\
-                    return true;                                                                             \
-                }                                                                                            \
-            }                                                                                                \
-            hm ? bwd_v2_launch<T, DD, LL, PP, 8, true>(ARGS) : bwd_v2_launch<T, DD, LL, PP, 8, false>(ARGS);  \
-            return true;                                                                                     \
-        }                                                                                                    \
-    }
-    MSDA_FOR_EACH_SPEC(X)
-#undef X
-#undef ARGS
-    return false;
-}
-
-// ---- v5: lean kernels (2-D grid, 32-bit offsets, all-taps-valid fast path) ---------------------------
-std::atomic<int> g_hoist{0};  // v5 forward: issue all tap loads of a row before consuming any
-
+// ---- row kernels (msda_kernels_v5.cuh) ---------------------------------------------------------------
 template <typename T, int DD, int LL, int PP, int W>
 void fwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                    const void *attn, void *out, cudaStream_t st)
 {
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
-    constexpr bool kFlagship = DD == 32 && LL == 4 && PP == 4;  // the A/B variants exist for this shape only
+    constexpr bool kFlagship = DD == 32 && LL == 4 && PP == 4;  // the hoisted A/B variant exists for this shape only
     bool hoist = false;
     if constexpr (kFlagship) hoist = g_hoist.load() != 0;
     if constexpr (kFlagship) {
@@ -327,33 +187,34 @@ struct BwdChunk<__nv_bfloat16> {
     using type = msda::ChunkBf16x4;
 };
 
+// skip_budget > 0: levels whose fp32 plane fits that many bytes get their grad_value from another kernel
 template <typename T, int DD, int LL, int PP, int W>
 void bwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                    const void *attn, const void *gout, void *gv_acc, const float *det_scale, void *gloc, void *gattn,
-                   cudaStream_t st)
+                   int skip_budget, cudaStream_t st)
 {
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
     using CH = typename BwdChunk<T>::type;
+    constexpr bool kHasSkip = (DD == 32 || DD == 64) && LL == 4 && PP == 4 && W == 4;
     if (det_scale)
         msda::msda_bwd_v5<T, CH, msda::AccFix64, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout,
             (unsigned long long *)gv_acc, det_scale, (float *)gloc, (float *)gattn, (int)d->spatial_size,
-            (int)d->num_heads, rpi);
-    else
+            (int)d->num_heads, rpi, 0);
+    else if (skip_budget > 0) {
+        if constexpr (kHasSkip)
+            msda::msda_bwd_v5<T, CH, msda::AccF32, DD, LL, PP, W, true><<<grid, W * 32, 0, st>>>(
+                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout,
+                (float *)gv_acc, nullptr, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi,
+                skip_budget);
+    } else
         msda::msda_bwd_v5<T, CH, msda::AccF32, DD, LL, PP, W><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, (float *)gv_acc,
-            nullptr, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi);
+            nullptr, (float *)gloc, (float *)gattn, (int)d->spatial_size, (int)d->num_heads, rpi, 0);
     snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v5<%s,D%d,L%d,P%d,w%d%s>", tname<T>(), DD, LL, PP, W,
              det_scale ? ",deterministic" : "");
 }
-
-// v5-only specialisations: L*P that is not a power of two (3- and 5-level pyramids)
-#define MSDA_FOR_EACH_V5_EXTRA_SPEC(X) \
-    X(32, 3, 4)                        \
-    X(64, 3, 4)                        \
-    X(32, 5, 4)                        \
-    X(64, 5, 4)
 
 template <int DD, int LL, int PP, int E>
 constexpr bool v5_ok()
@@ -367,7 +228,6 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
                    const void *attn, void *out, cudaStream_t st)
 {
     constexpr int E = msda::Chunk<T>::E;
-    if (d->batch > 65535) return false;  // gridDim.y
     const bool w8 = g_warps.load() >= 8;
 #define X(DD, LL, PP)                                                                                  \
     if constexpr (v5_ok<DD, LL, PP, E>()) {                                                            \
@@ -383,7 +243,6 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
         }                                                                                              \
     }
     MSDA_FOR_EACH_SPEC(X)
-    MSDA_FOR_EACH_V5_EXTRA_SPEC(X)
 #undef X
     return false;
 }
@@ -391,141 +250,192 @@ bool launch_fwd_v5(const msda_dims *d, const void *value, const int64_t *shapes,
 template <typename T>
 bool launch_bwd_v5(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                    const void *attn, const void *gout, void *gv_acc, const float *det_scale, void *gloc, void *gattn,
-                   cudaStream_t st)
+                   int skip_budget, cudaStream_t st)
 {
     constexpr int E = BwdChunk<T>::type::E;
-    if (d->batch > 65535) return false;
-    const bool w8 = g_warps.load() >= 8;
+    const bool w8 = g_warps.load() >= 8 && skip_budget == 0;
 #define X(DD, LL, PP)                                                                                             \
     if constexpr (v5_ok<DD, LL, PP, E>()) {                                                                       \
         if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                              \
             if constexpr ((DD) == 32 && (LL) == 4 && (PP) == 4) {                                                 \
                 if (w8) {                                                                                         \
                     bwd_v5_launch<T, DD, LL, PP, 8>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale,    \
-                                                    gloc, gattn, st);                                             \
+                                                    gloc, gattn, 0, st);                                          \
                     return true;                                                                                  \
                 }                                                                                                 \
             }                                                                                                     \
             bwd_v5_launch<T, DD, LL, PP, 4>(d, value, shapes, lsi, loc, attn, gout, gv_acc, det_scale, gloc,      \
-                                            gattn, st);                                                           \
+                                            gattn, skip_budget, st);                                              \
             return true;                                                                                          \
         }                                                                                                         \
     }
     MSDA_FOR_EACH_SPEC(X)
-    MSDA_FOR_EACH_V5_EXTRA_SPEC(X)
 #undef X
     return false;
 }
 
-// ---- v3: persistent CTAs with shared-memory staging ------------------------------------------------
-struct DeviceInfo {
-    int sms = 0;
-    int max_smem_optin = 0;
-};
-
-const DeviceInfo &device_info()
-{
-    thread_local DeviceInfo cache[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    DeviceInfo &d = cache[dev & 63];
-    if (d.sms == 0) {
-        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
-    return d;
-}
-
-bool v3_wanted(const msda_dims *d)
-{
-    const int v = g_variant.load();
-    if (v == 3) return true;
-    if (v != 0) return false;
-    const DeviceInfo &di = device_info();
-    return di.sms > 0 && d->num_heads * d->num_query / di.sms >= g_v3_min_rows.load();
-}
-
+// ---- persistent shared-memory-staged forward (msda_kernels_staged.cuh) ---------------------------------
 template <typename K>
-int v3_prepare(K kernel, int *smem_bytes)
+int optin_smem(K kernel, int bytes)
 {
-    const DeviceInfo &di = device_info();
-    *smem_bytes = di.max_smem_optin - 1024;  // leave room for the kernel's static shared memory
-    if (*smem_bytes <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
-    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, *smem_bytes),
-                      "cudaFuncSetAttribute(v3)");
+    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes),
+                      "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
 }
 
 template <typename T, int DD, int LL, int PP, int TH>
-int fwd_v3_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                  const void *attn, void *out, cudaStream_t st)
+int fwd_staged_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                      const void *attn, void *out, cudaStream_t st)
 {
     auto kernel = msda::msda_fwd_v3<T, DD, LL, PP, TH>;
-    int smem = 0;
-    if (int rc = v3_prepare(kernel, &smem)) return rc;
+    const int smem = device_info().max_smem_optin - 1024;  // leave room for the kernel's static shared memory
+    if (smem <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
+    if (int rc = optin_smem(kernel, smem)) return rc;
     kernel<<<device_info().sms, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc,
                                                 (const float *)attn, (T *)out, (int)d->batch, (int)d->spatial_size,
                                                 (int)d->num_heads, (int)d->num_query, smem / (int)sizeof(T));
-    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v3<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_staged<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
     return MSDA_OK;
 }
 
-template <typename T, int DD, int LL, int PP, int TH>
-int bwd_v3_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                  const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
-{
-    auto kernel = msda::msda_bwd_v3<T, DD, LL, PP, TH>;
-    int smem = 0;
-    if (int rc = v3_prepare(kernel, &smem)) return rc;
-    kernel<<<device_info().sms, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc,
-                                                (const float *)attn, (const T *)gout, gv_acc, (float *)gloc,
-                                                (float *)gattn, (int)d->batch, (int)d->spatial_size,
-                                                (int)d->num_heads, (int)d->num_query, smem / (int)sizeof(float));
-    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v3<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
-    return MSDA_OK;
-}
-
-#define MSDA_FOR_EACH_V3_SPEC(X) \
-    X(32, 4, 4)                  \
-    X(64, 4, 4)
-
-// returns -1 when no v3 specialisation matches, else a status code
+// returns -1 when no staged specialisation matches, else a status code
 template <typename T>
-int launch_fwd_v3(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                  const void *attn, void *out, cudaStream_t st)
+int launch_fwd_staged(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                      const void *attn, void *out, cudaStream_t st)
 {
-    constexpr int E = msda::Chunk<T>::E;
     const int th = g_v3_threads.load();
-#define X(DD, LL, PP)                                                                                     \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                               \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                        \
-            return th >= 1024  ? fwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, out, st) \
-                   : th >= 768 ? fwd_v3_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, out, st)  \
-                               : fwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, out, st); \
-    }
-    MSDA_FOR_EACH_V3_SPEC(X)
+#define X(DD, LL, PP)                                                                                         \
+    if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                                \
+        return th >= 1024  ? fwd_staged_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, out, st) \
+               : th >= 768 ? fwd_staged_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, out, st)  \
+                           : fwd_staged_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, out, st);
+    MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
 #undef X
     return -1;
+}
+
+// ---- grad_value by on-SM aggregation (msda_kernels_binned.cuh) -------------------------------------------
+enum { BWD_ROW = 1, BWD_BINNED = 2, BWD_OWNED = 3 };
+
+bool flagship_spec(const msda_dims *d)
+{
+#define X(DD, LL, PP) \
+    if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) return true;
+    MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
+#undef X
+    return false;
+}
+
+struct BinnedPlan {
+    int smem_bytes, region_bytes, acc_budget, bins_cap;
+};
+
+// Shared-memory split of msda_bwd_binned for channel width D and P points (see the layout comment at the kernel).
+bool binned_plan(int D, int P, BinnedPlan *bp)
+{
+    const int total = (device_info().max_smem_optin - 1024) & ~15;
+    const int min_tile = (msda::kBinThreads / P) * (D * 4 + P * 16);
+    // region + 4 * (2 * bins_cap + 4) <= total with bins_cap = (region - min_tile) / (2 D) + 2
+    long long region = ((long long)(total - 32) * D + 4LL * min_tile) / (D + 4);
+    region &= ~15LL;
+    for (;; region -= 16) {
+        if (region <= min_tile) return false;
+        const long long budget = region - min_tile;
+        const long long bins = budget / (2 * D) + 2;
+        if (region + 4 * (2 * bins + 4) <= total) {
+            bp->smem_bytes = total, bp->region_bytes = (int)region, bp->acc_budget = (int)budget, bp->bins_cap = (int)bins;
+            return true;
+        }
+    }
+}
+
+struct OwnedPlan {
+    int smem_bytes, chunks, chunk_pixels, tq;
+};
+
+bool owned_plan(const msda_dims *d, OwnedPlan *op)
+{
+    const int total = (device_info().max_smem_optin - 1024) & ~15;
+    const int64_t S = d->spatial_size, Lq = d->num_query;
+    const int64_t per_row = d->channels * 4 + d->num_levels * d->num_point * 32;
+    int64_t chunks = (8LL * device_info().sms + d->batch * d->num_heads - 1) / (d->batch * d->num_heads);
+    if (chunks < 1) chunks = 1;
+    if (chunks > S) chunks = S > 0 ? S : 1;
+    for (;; chunks *= 2) {
+        const int64_t cp = (S + chunks - 1) / chunks;
+        const int64_t cur_bytes = ((cp + 1) * 4 + 15) & ~15LL;
+        const int64_t rows_fit = (total - cur_bytes) / per_row;
+        const int64_t want = Lq < 32 ? (Lq > 0 ? Lq : 1) : 32;
+        if (total > cur_bytes && rows_fit >= want) {
+            op->smem_bytes = total;
+            op->chunks = (int)chunks, op->chunk_pixels = (int)cp;
+            op->tq = (int)(rows_fit < Lq ? rows_fit : (Lq > 0 ? Lq : 1));
+            return true;
+        }
+        if (cp <= 1) return false;
+    }
+}
+
+// The backward strategy for this problem.  Pure function of (dims, dtype, flags, knobs): msda_backward_workspace_bytes
+// relies on that.
+int choose_bwd_mode(const msda_dims *d, int dtype, unsigned flags)
+{
+    if ((flags & MSDA_FLAG_DETERMINISTIC) || !vec_eligible(d, dtype, flags) || !flagship_spec(d)) return BWD_ROW;
+    if (d->batch * d->num_query * d->num_heads == 0 || d->spatial_size == 0) return BWD_ROW;
+    const int forced = g_bwd_mode.load();
+    if (forced == BWD_ROW) return BWD_ROW;
+    BinnedPlan bp;
+    OwnedPlan op;
+    const bool can_bin = binned_plan((int)d->channels, (int)d->num_point, &bp);
+    const bool can_own = owned_plan(d, &op);
+    if (forced == BWD_BINNED) return can_bin ? BWD_BINNED : BWD_ROW;
+    if (forced == BWD_OWNED) return can_own ? BWD_OWNED : BWD_ROW;
+    const int64_t taps = d->num_query * d->num_levels * d->num_point * 4;
+    if (can_own && taps <= (int64_t)g_owned_max_taps.load() * d->spatial_size) return BWD_OWNED;
+    if (can_bin && d->num_levels >= 2 && d->num_query >= g_bin_min_rows.load()) return BWD_BINNED;
+    return BWD_ROW;
 }
 
 template <typename T>
-int launch_bwd_v3(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
-                  const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+int launch_bwd_binned(const msda_dims *d, const BinnedPlan &bp, const int64_t *shapes, const int64_t *lsi,
+                      const void *loc, const void *attn, const void *gout, float *gv_acc, cudaStream_t st)
 {
-    constexpr int E = msda::Chunk<T>::E;
-    const bool big = g_v3_threads.load() >= 1024;
-#define X(DD, LL, PP)                                                                                                \
-    if constexpr (v2_ok<DD, LL, PP, E>()) {                                                                          \
-        if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                                   \
-            return big ? bwd_v3_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc,    \
-                                                            gattn, st)                                               \
-                       : bwd_v3_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc,     \
-                                                           gattn, st);                                               \
+#define X(DD, LL, PP)                                                                                              \
+    if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                                   \
+        auto kernel = msda::msda_bwd_binned<T, DD, LL, PP>;                                                        \
+        if (int rc = optin_smem(kernel, bp.smem_bytes)) return rc;                                                 \
+        kernel<<<device_info().sms, msda::kBinThreads, bp.smem_bytes, st>>>(                                       \
+            shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, gv_acc, (int)d->batch,          \
+            (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, bp.acc_budget, bp.region_bytes, bp.bins_cap); \
+        return MSDA_OK;                                                                                            \
     }
-    MSDA_FOR_EACH_V3_SPEC(X)
+    MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
 #undef X
-    return -1;
+    return fail(MSDA_ERR_UNSUPPORTED, "no binned backward for this shape");
 }
 
+template <typename T>
+int launch_bwd_owned(const msda_dims *d, const OwnedPlan &op, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                     const void *attn, const void *gout, void *grad_value, int accumulate, cudaStream_t st)
+{
+    const int64_t items = d->batch * d->num_heads * op.chunks;
+    const int64_t cap = (int64_t)device_info().sms;
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+#define X(DD, LL, PP)                                                                                              \
+    if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP)) {                                   \
+        auto kernel = msda::msda_bwd_owned<T, DD, LL, PP>;                                                         \
+        if (int rc = optin_smem(kernel, op.smem_bytes)) return rc;                                                 \
+        kernel<<<grid, msda::kBinThreads, op.smem_bytes, st>>>(                                                    \
+            shapes, lsi, (const float *)loc, (const float *)attn, (const T *)gout, (T *)grad_value, (int)d->batch, \
+            (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, op.chunks, op.chunk_pixels, op.tq,         \
+            accumulate);                                                                                           \
+        return MSDA_OK;                                                                                            \
+    }
+    MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
+#undef X
+    return fail(MSDA_ERR_UNSUPPORTED, "no owned backward for this shape");
+}
+
+// ---- generic kernels -----------------------------------------------------------------------------------------------
 template <typename T, typename C>
 void launch_fwd_generic(const msda_dims *d, const Geometry &g, const void *value, const int64_t *shapes,
                         const int64_t *lsi, const void *loc, const void *attn, void *out, cudaStream_t st,
@@ -575,11 +485,12 @@ int msda_set_tuning(const char *key, int value)
 {
     std::atomic<int> *knob = nullptr;
     if (key && !strcmp(key, "variant")) knob = &g_variant;
-    if (key && !strcmp(key, "head_major")) knob = &g_head_major;
     if (key && !strcmp(key, "warps")) knob = &g_warps;
     if (key && !strcmp(key, "v3_threads")) knob = &g_v3_threads;
     if (key && !strcmp(key, "hoist")) knob = &g_hoist;
-    if (key && !strcmp(key, "v3_min_rows")) knob = &g_v3_min_rows;
+    if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
+    if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
+    if (key && !strcmp(key, "owned_max_taps")) knob = &g_owned_max_taps;
     if (!knob) return -1;
     return knob->exchange(value);
 }
@@ -608,46 +519,20 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        if (v3_wanted(dims) && dims->batch < (1 << 30) && dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
+        if (g_variant.load() == 3) {
             const int rc = dtype == MSDA_F32
-                               ? launch_fwd_v3<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                                      attn_weight, output, st)
-                               : launch_fwd_v3<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
-                                                              sampling_loc, attn_weight, output, st);
+                               ? launch_fwd_staged<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                          attn_weight, output, st)
+                               : launch_fwd_staged<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
+                                                                  sampling_loc, attn_weight, output, st);
             if (rc > 0) return rc;
             done = rc == 0;
         }
-        if (!done && g_variant.load() == 5)
+        if (!done)
             done = dtype == MSDA_F32 ? launch_fwd_v5<float>(dims, value, spatial_shapes, level_start_index,
                                                            sampling_loc, attn_weight, output, st)
                                      : launch_fwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
                                                                    sampling_loc, attn_weight, output, st);
-        if (!done && g_variant.load() == 4 && dims->channels == 32 && dims->num_levels == 4 && dims->num_point == 4 &&
-            dtype == MSDA_F32) {
-            const int w = g_warps.load();
-            if (w == 4)
-                fwd_v2p_launch<float, 32, 4, 4, 4>(dims, g.rows, value, spatial_shapes, level_start_index,
-                                                   sampling_loc, attn_weight, output, st);
-            else if (w == 16)
-                fwd_v2p_launch<float, 32, 4, 4, 16>(dims, g.rows, value, spatial_shapes, level_start_index,
-                                                    sampling_loc, attn_weight, output, st);
-            else
-                fwd_v2p_launch<float, 32, 4, 4, 8>(dims, g.rows, value, spatial_shapes, level_start_index,
-                                                   sampling_loc, attn_weight, output, st);
-            done = true;
-        }
-        if (!done && g_variant.load() != 1) {
-            done = dtype == MSDA_F32 ? launch_fwd_v2<float>(dims, g, value, spatial_shapes, level_start_index,
-                                                           sampling_loc, attn_weight, output, st)
-                                     : launch_fwd_v2<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index,
-                                                                   sampling_loc, attn_weight, output, st);
-        }
-        if (!done)
-            done = dtype == MSDA_F32 ? launch_fwd_vec<float>(dims, g, value, spatial_shapes, level_start_index,
-                                                            sampling_loc, attn_weight, output, st)
-                                     : launch_fwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes,
-                                                                    level_start_index, sampling_loc, attn_weight,
-                                                                    output, st);
     }
     if (!done) {
         if (dtype == MSDA_F32)
@@ -670,7 +555,14 @@ size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned 
     const size_t n_value = (size_t)(dims->batch * dims->spatial_size * dims->num_heads * dims->channels);
     if ((flags & MSDA_FLAG_DETERMINISTIC) && dtype != MSDA_F64)
         return n_value * sizeof(long long) + 16;  // int64 fixed-point accumulators + {max|attn|, max|g|, 2^k, 2^-k}
-    if (dtype == MSDA_BF16) return n_value * sizeof(float);  // fp32 accumulation image of grad_value
+    if (dtype == MSDA_BF16) {
+        // the owned backward writes bf16 grad_value directly; it needs 16-byte aligned tensors, which the caller vouches
+        // for with MSDA_FLAG_ALIGNED16 (otherwise the answer stays conservative)
+        if ((flags & MSDA_FLAG_ALIGNED16) && check_dims(dims, dtype) == MSDA_OK &&
+            choose_bwd_mode(dims, dtype, flags) == BWD_OWNED)
+            return 0;
+        return n_value * sizeof(float);  // fp32 accumulation image of grad_value
+    }
     return 0;
 }
 
@@ -701,6 +593,8 @@ int acc_begin(const msda_dims *dims, const Geometry &g, int dtype, unsigned flag
     if (!workspace || workspace_bytes < need)
         return fail(MSDA_ERR_WORKSPACE, "this backward needs a %zu-byte workspace, got %zu", need, workspace_bytes);
     if (!aligned16(workspace)) return fail(MSDA_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+    if (dtype == MSDA_BF16 && !plan->det && !aligned16(grad_value))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "bf16 grad_value must be 16-byte aligned (vector fold)");
     if (int rc = check_cuda(cudaMemsetAsync(workspace, 0, need, st), "memset workspace")) return rc;
     plan->gv_acc = workspace;
     if (plan->det) {
@@ -708,7 +602,7 @@ int acc_begin(const msda_dims *dims, const Geometry &g, int dtype, unsigned flag
         plan->det_scale = reinterpret_cast<const float *>(plan->tail) + 2;
         const int64_t n_attn = attn ? g.rows * dims->num_levels * dims->num_point : 0;
         const int64_t n_gout = g.rows * dims->channels;
-        const int blocks = 148 * 8;
+        const int blocks = device_info().sms * 8;
         if (dtype == MSDA_F32)
             msda::msda_det_absmax<float><<<blocks, 256, 0, st>>>((const float *)attn, n_attn,
                                                                  (const float *)grad_output, n_gout, plan->tail);
@@ -732,7 +626,7 @@ int acc_end(const msda_dims *dims, int dtype, unsigned flags, void *grad_value, 
     const int threads = 256;
     const int accumulate = (flags & MSDA_FLAG_ZERO_GRAD_VALUE) ? 0 : 1;
     if (plan.det) {
-        const int blocks = 148 * 16;
+        const int blocks = device_info().sms * 16;
         if (dtype == MSDA_F32)
             msda::msda_det_fold<float><<<blocks, threads, 0, st>>>((const long long *)workspace,
                                                                   (const float *)plan.tail, (float *)grad_value,
@@ -744,7 +638,7 @@ int acc_end(const msda_dims *dims, int dtype, unsigned flags, void *grad_value, 
     } else {
         int64_t blocks = (n_value / 8 + threads - 1) / threads;
         if (blocks < 1) blocks = 1;
-        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks > device_info().sms * 16) blocks = device_info().sms * 16;
         msda::msda_fold_workspace_bf16<<<(unsigned)blocks, threads, 0, st>>>(
             (const float *)workspace, (__nv_bfloat16 *)grad_value, n_value, accumulate);
     }
@@ -754,7 +648,7 @@ int acc_end(const msda_dims *dims, int dtype, unsigned flags, void *grad_value, 
 
 // zero-fills shared by the plain and the fused backward; returns 1 when there is nothing left to launch
 int backward_prologue(const msda_dims *dims, const Geometry &g, int dtype, unsigned flags, void *grad_value,
-                      void *grad_pts2, void *grad_pts1, cudaStream_t st, int *rc_out)
+                      void *grad_pts2, void *grad_pts1, cudaStream_t st, int *rc_out, bool writes_everything = false)
 {
     const int64_t n_value = dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
     const bool via_workspace = (flags & MSDA_FLAG_DETERMINISTIC) || dtype == MSDA_BF16;
@@ -763,7 +657,7 @@ int backward_prologue(const msda_dims *dims, const Geometry &g, int dtype, unsig
         *rc_out = fail(MSDA_ERR_INVALID_ARGUMENT, "grad_value is null");
         return 1;
     }
-    if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && (!via_workspace || g.rows == 0))
+    if ((flags & MSDA_FLAG_ZERO_GRAD_VALUE) && n_value > 0 && ((!via_workspace && !writes_everything) || g.rows == 0))
         if ((*rc_out = check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)n_value * dtype_size(dtype), st),
                                   "memset grad_value")))
             return 1;
@@ -800,11 +694,47 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     Geometry g;
     if (int rc = geometry(dims, &g)) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
+
+    const bool vec_ok = vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) &&
+                        (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
+                        (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0;
+    int mode = vec_ok ? choose_bwd_mode(dims, dtype, flags) : BWD_ROW;
+    if (mode == BWD_OWNED && !aligned16(grad_value)) mode = BWD_ROW;
+    BinnedPlan bp{};
+    OwnedPlan op{};
+    if (mode == BWD_BINNED && !binned_plan((int)dims->channels, (int)dims->num_point, &bp)) mode = BWD_ROW;
+    if (mode == BWD_OWNED && !owned_plan(dims, &op)) mode = BWD_ROW;
+
     int rc0 = MSDA_OK;
-    if (backward_prologue(dims, g, dtype, flags, grad_value, grad_sampling_loc, grad_attn_weight, st, &rc0)) return rc0;
+    if (backward_prologue(dims, g, dtype, flags, grad_value, grad_sampling_loc, grad_attn_weight, st, &rc0,
+                          mode == BWD_OWNED))
+        return rc0;
     if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output ||
         !grad_sampling_loc || !grad_attn_weight)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+
+    if (mode == BWD_OWNED) {
+        // every line of grad_value is written once by its owner: no zero-fill, no workspace, no fold
+        bool ok = dtype == MSDA_F32
+                      ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                             grad_output, grad_value, nullptr, grad_sampling_loc, grad_attn_weight,
+                                             0x7fffffff, st)
+                      : launch_bwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                     attn_weight, grad_output, grad_value, nullptr, grad_sampling_loc,
+                                                     grad_attn_weight, 0x7fffffff, st);
+        if (!ok) return fail(MSDA_ERR_UNSUPPORTED, "owned backward: no row kernel for this shape");
+        const int accumulate = (flags & MSDA_FLAG_ZERO_GRAD_VALUE) ? 0 : 1;
+        const int rc = dtype == MSDA_F32
+                           ? launch_bwd_owned<float>(dims, op, spatial_shapes, level_start_index, sampling_loc,
+                                                     attn_weight, grad_output, grad_value, accumulate, st)
+                           : launch_bwd_owned<__nv_bfloat16>(dims, op, spatial_shapes, level_start_index, sampling_loc,
+                                                             attn_weight, grad_output, grad_value, accumulate, st);
+        if (rc) return rc;
+        tl_launches += 2;
+        snprintf(tl_kernel, sizeof(tl_kernel), "bwd_v5+owned<%s,D%d,L%d,P%d>", dtype_name(dtype), (int)dims->channels,
+                 (int)dims->num_levels, (int)dims->num_point);
+        return check_cuda(cudaPeekAtLastError(), "msda_backward launch");
+    }
 
     AccPlan plan;
     if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, attn_weight, grad_output, st,
@@ -814,47 +744,26 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     const float *det_scale = plan.det_scale;
 
     bool done = false;
-    const int variant = g_variant.load();
-    if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(grad_output) && aligned16(gv_acc) &&
-        (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0 &&
-        (reinterpret_cast<uintptr_t>(grad_sampling_loc) & 7u) == 0) {
-        if (!det && v3_wanted(dims) && dims->batch < (1 << 30) &&
-            dims->num_heads * dims->num_query < ((int64_t)1 << 31)) {
-            const int rc =
-                dtype == MSDA_F32
-                    ? launch_bwd_v3<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
-                                           grad_output, (float *)gv_acc, grad_sampling_loc, grad_attn_weight, st)
-                    : launch_bwd_v3<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                                   attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
-                                                   grad_attn_weight, st);
-            if (rc > 0) return rc;
-            done = rc == 0;
+    if (vec_ok && aligned16(gv_acc)) {
+        const int skip = mode == BWD_BINNED ? bp.acc_budget : 0;
+        done = dtype == MSDA_F32
+                   ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                          grad_output, gv_acc, det_scale, grad_sampling_loc, grad_attn_weight, skip, st)
+                   : launch_bwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                  attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
+                                                  grad_attn_weight, skip, st);
+        if (done && mode == BWD_BINNED) {
+            const int rc = dtype == MSDA_F32
+                               ? launch_bwd_binned<float>(dims, bp, spatial_shapes, level_start_index, sampling_loc,
+                                                          attn_weight, grad_output, (float *)gv_acc, st)
+                               : launch_bwd_binned<__nv_bfloat16>(dims, bp, spatial_shapes, level_start_index,
+                                                                  sampling_loc, attn_weight, grad_output,
+                                                                  (float *)gv_acc, st);
+            if (rc) return rc;
+            ++tl_launches;
+            const size_t n = strlen(tl_kernel);
+            snprintf(tl_kernel + n, sizeof(tl_kernel) - n, "+binned");
         }
-        if (!done && (variant == 5 || det))  // the deterministic accumulator exists in the v5 and generic kernels
-            done = dtype == MSDA_F32
-                       ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                              attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
-                                              grad_attn_weight, st)
-                       : launch_bwd_v5<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index, sampling_loc,
-                                                      attn_weight, grad_output, gv_acc, det_scale, grad_sampling_loc,
-                                                      grad_attn_weight, st);
-        if (!done && !det && variant != 1) {
-            done = dtype == MSDA_F32
-                       ? launch_bwd_v2<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                              attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
-                                              grad_attn_weight, st)
-                       : launch_bwd_v2<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                                      attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
-                                                      grad_attn_weight, st);
-        }
-        if (!done && !det)
-            done = dtype == MSDA_F32
-                       ? launch_bwd_vec<float>(dims, g, value, spatial_shapes, level_start_index, sampling_loc,
-                                               attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
-                                               grad_attn_weight, st)
-                       : launch_bwd_vec<__nv_bfloat16>(dims, g, value, spatial_shapes, level_start_index,
-                                                       sampling_loc, attn_weight, grad_output, (float *)gv_acc,
-                                                       grad_sampling_loc, grad_attn_weight, st);
     }
     if (!done) {
         if (dtype == MSDA_F32)
@@ -877,9 +786,7 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
 
 // ---- fused module path (softmax + sampling-location arithmetic inside the kernels) --------------------------------
 
-#define MSDA_FOR_EACH_FUSED_SPEC(X) \
-    X(32, 4, 4)                     \
-    X(64, 4, 4)
+#define MSDA_FOR_EACH_FUSED_SPEC(X) MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
 
 int msda_pack_levels(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch, int64_t channels,
                      void *memory, int dtype, int unpack, void *cuda_stream)
@@ -944,7 +851,7 @@ int msda_probe_ceiling(int which, void *scratch, size_t scratch_bytes, int64_t *
 int msda_fused_supported(const msda_dims *dims, int dtype, int ref_dim)
 {
     if (!dims || (dtype != MSDA_F32 && dtype != MSDA_BF16) || (ref_dim != 2 && ref_dim != 4)) return 0;
-    if (!vec_eligible(dims, dtype, 0) || dims->batch > 65535) return 0;
+    if (!vec_eligible(dims, dtype, 0)) return 0;
 #define X(DD, LL, PP) \
     if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) return 1;
     MSDA_FOR_EACH_FUSED_SPEC(X)
@@ -960,7 +867,7 @@ int msda_mask_rows(void *data, const unsigned char *mask, int64_t n_rows, int64_
     if (row_bytes % 16 != 0 || !aligned16(data) || row_bytes > 0x7fffffff)
         return fail(MSDA_ERR_UNSUPPORTED, "msda_mask_rows needs 16-byte aligned rows");
     int64_t blocks = (n_rows + 7) / 8;
-    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks > device_info().sms * 32) blocks = device_info().sms * 32;
     msda::msda_mask_rows<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)cuda_stream>>>((float *)data, mask, n_rows,
                                                                                          (int)row_bytes);
     ++tl_launches;
@@ -1075,13 +982,14 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
     if (!value || !spatial_shapes || !level_start_index || !sampling_offsets || !attn_logits || !reference_points ||
         !grad_output || !grad_offsets || !grad_logits)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value) || !aligned16(workspace) ||
+        !aligned16(reference_points) || (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u) ||
+        (reinterpret_cast<uintptr_t>(grad_offsets) & 7u))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned tensors");
     AccPlan plan;
     if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, nullptr, grad_output, st,
                            &plan))
         return rc;
-    if (!aligned16(value) || !aligned16(grad_output) || !aligned16(plan.gv_acc) || !aligned16(reference_points) ||
-        (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u) || (reinterpret_cast<uintptr_t>(grad_offsets) & 7u))
-        return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned tensors");
 #define ARGS                                                                                                    \
     dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output, \
         plan.gv_acc, plan.det_scale, grad_offsets, grad_logits, st
@@ -1111,6 +1019,9 @@ struct msda_host_session {
     int dtype;
     int device;
     int chunk;  // images per chunk
+    int next_slot;  // round-robin cursor; persists across submits so consecutive calls keep the pipeline full
+    int meta_levels;  // number of levels currently uploaded (0 = none)
+    int64_t h_shapes[2 * 64], h_lsi[64];  // host copy of the uploaded level metadata
     int64_t *d_shapes, *d_lsi;
     cudaStream_t stream[kMaxSlots];
     struct Slot {
@@ -1143,6 +1054,7 @@ int msda_host_session_create(msda_host_session **session, const msda_dims *max_d
     *session = nullptr;
     if (int rc = check_dims(max_dims, dtype)) return rc;
     if (images_per_chunk <= 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "images_per_chunk must be positive");
+    if (max_dims->num_levels > 64) return fail(MSDA_ERR_UNSUPPORTED, "host sessions support at most 64 levels");
     if (int rc = check_cuda(cudaSetDevice(device), "cudaSetDevice")) return rc;
     auto *s = new msda_host_session();
     memset(s, 0, sizeof(*s));
@@ -1190,10 +1102,10 @@ int msda_host_session_create(msda_host_session **session, const msda_dims *max_d
 
 void msda_host_session_destroy(msda_host_session *session) { session_free(session); }
 
-int msda_host_forward_backward(msda_host_session *s, const void *value, const int64_t *spatial_shapes,
-                               const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
-                               const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
-                               void *grad_attn_weight, const msda_dims *dims, unsigned flags)
+int msda_host_submit(msda_host_session *s, const void *value, const int64_t *spatial_shapes,
+                     const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                     const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                     void *grad_attn_weight, const msda_dims *dims, unsigned flags)
 {
     tl_error[0] = 0;
     if (!s) return fail(MSDA_ERR_INVALID_ARGUMENT, "session is null");
@@ -1206,6 +1118,9 @@ int msda_host_forward_backward(msda_host_session *s, const void *value, const in
         dims->spatial_size * dims->num_heads * dims->channels > mx.spatial_size * mx.num_heads * mx.channels ||
         dims->num_levels > mx.num_levels)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "problem exceeds the session's max_dims");
+    if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !grad_output || !output ||
+        !grad_value || !grad_sampling_loc || !grad_attn_weight)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null host pointer");
     if (int rc = check_cuda(cudaSetDevice(s->device), "cudaSetDevice")) return rc;
 
     const size_t ev = dtype_size(s->dtype), el = s->dtype == MSDA_F64 ? 8 : 4;
@@ -1213,50 +1128,80 @@ int msda_host_forward_backward(msda_host_session *s, const void *value, const in
     const size_t img_pts = (size_t)(dims->num_query * dims->num_heads * dims->num_levels * dims->num_point) * el;
     const size_t img_out = (size_t)(dims->num_query * dims->num_heads * dims->channels) * ev;
     const int K = s->n_slots;
+    const int L = (int)dims->num_levels;
 
-    // level metadata: one small upload, made visible to every slot stream through an event
-    cudaEvent_t meta_ready;
-    if (int rc = check_cuda(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming), "event")) return rc;
-    cudaMemcpyAsync(s->d_shapes, spatial_shapes, sizeof(int64_t) * 2 * dims->num_levels, cudaMemcpyHostToDevice,
-                    s->stream[0]);
-    cudaMemcpyAsync(s->d_lsi, level_start_index, sizeof(int64_t) * dims->num_levels, cudaMemcpyHostToDevice,
-                    s->stream[0]);
-    cudaEventRecord(meta_ready, s->stream[0]);
-    for (int i = 1; i < K; ++i) cudaStreamWaitEvent(s->stream[i], meta_ready, 0);
+    // Level metadata lives on the device for the whole session.  It is uploaded only when it changes; work already in
+    // flight may still be reading the old copy, so a change drains the pipeline first (rare: one pyramid per model).
+    bool meta_changed = s->meta_levels != L;
+    for (int i = 0; i < L && !meta_changed; ++i)
+        meta_changed = s->h_shapes[2 * i] != spatial_shapes[2 * i] || s->h_shapes[2 * i + 1] != spatial_shapes[2 * i + 1] ||
+                       s->h_lsi[i] != level_start_index[i];
+    cudaError_t e = cudaSuccess;
+    auto track = [&](cudaError_t ei) {
+        if (e == cudaSuccess) e = ei;
+    };
+    if (meta_changed) {
+        for (int i = 0; i < K; ++i) track(cudaStreamSynchronize(s->stream[i]));
+        memcpy(s->h_shapes, spatial_shapes, sizeof(int64_t) * 2 * L);
+        memcpy(s->h_lsi, level_start_index, sizeof(int64_t) * L);
+        s->meta_levels = L;
+        track(cudaMemcpyAsync(s->d_shapes, s->h_shapes, sizeof(int64_t) * 2 * L, cudaMemcpyHostToDevice, s->stream[0]));
+        track(cudaMemcpyAsync(s->d_lsi, s->h_lsi, sizeof(int64_t) * L, cudaMemcpyHostToDevice, s->stream[0]));
+        track(cudaStreamSynchronize(s->stream[0]));
+        if (e != cudaSuccess) return check_cuda(e, "msda_host_submit (level metadata)");
+    }
 
     int rc = MSDA_OK;
-    int slot = 0;
-    for (int64_t b0 = 0; b0 < dims->batch && rc == MSDA_OK; b0 += s->chunk, slot = (slot + 1) % K) {
+    for (int64_t b0 = 0; b0 < dims->batch && rc == MSDA_OK; b0 += s->chunk) {
         const int64_t nb = (dims->batch - b0 < s->chunk) ? dims->batch - b0 : s->chunk;
+        const int slot = s->next_slot;
+        s->next_slot = (slot + 1) % K;
         auto &k = s->slot[slot];
-        cudaStream_t st = s->stream[slot];
+        cudaStream_t st = s->stream[slot];  // stream order serialises successive uses of the slot's buffers
         msda_dims cd = *dims;
         cd.batch = nb;
-        const char *hv = (const char *)value + b0 * img_val;
-        cudaMemcpyAsync(k.value, hv, nb * img_val, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(k.loc, (const char *)sampling_loc + b0 * img_pts * 2, nb * img_pts * 2,
-                        cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(k.attn, (const char *)attn_weight + b0 * img_pts, nb * img_pts, cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(k.gout, (const char *)grad_output + b0 * img_out, nb * img_out, cudaMemcpyHostToDevice, st);
+        track(cudaMemcpyAsync(k.value, (const char *)value + b0 * img_val, nb * img_val, cudaMemcpyHostToDevice, st));
+        track(cudaMemcpyAsync(k.loc, (const char *)sampling_loc + b0 * img_pts * 2, nb * img_pts * 2,
+                              cudaMemcpyHostToDevice, st));
+        track(cudaMemcpyAsync(k.attn, (const char *)attn_weight + b0 * img_pts, nb * img_pts, cudaMemcpyHostToDevice, st));
+        track(cudaMemcpyAsync(k.gout, (const char *)grad_output + b0 * img_out, nb * img_out, cudaMemcpyHostToDevice, st));
         rc = msda_forward(k.value, s->d_shapes, s->d_lsi, k.loc, k.attn, k.out, &cd, s->dtype, flags, st);
         if (rc) break;
         rc = msda_backward(k.value, s->d_shapes, s->d_lsi, k.loc, k.attn, k.gout, k.gvalue, k.gloc, k.gattn, &cd,
                            s->dtype, flags | MSDA_FLAG_ZERO_GRAD_VALUE, k.ws, s->ws_bytes, st);
         if (rc) break;
-        cudaMemcpyAsync((char *)output + b0 * img_out, k.out, nb * img_out, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync((char *)grad_value + b0 * img_val, k.gvalue, nb * img_val, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync((char *)grad_sampling_loc + b0 * img_pts * 2, k.gloc, nb * img_pts * 2,
-                        cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync((char *)grad_attn_weight + b0 * img_pts, k.gattn, nb * img_pts, cudaMemcpyDeviceToHost, st);
+        track(cudaMemcpyAsync((char *)output + b0 * img_out, k.out, nb * img_out, cudaMemcpyDeviceToHost, st));
+        track(cudaMemcpyAsync((char *)grad_value + b0 * img_val, k.gvalue, nb * img_val, cudaMemcpyDeviceToHost, st));
+        track(cudaMemcpyAsync((char *)grad_sampling_loc + b0 * img_pts * 2, k.gloc, nb * img_pts * 2,
+                              cudaMemcpyDeviceToHost, st));
+        track(cudaMemcpyAsync((char *)grad_attn_weight + b0 * img_pts, k.gattn, nb * img_pts, cudaMemcpyDeviceToHost, st));
     }
+    if (rc) return rc;
+    return check_cuda(e, "msda_host_submit");
+}
+
+int msda_host_wait(msda_host_session *s)
+{
+    tl_error[0] = 0;
+    if (!s) return fail(MSDA_ERR_INVALID_ARGUMENT, "session is null");
+    if (int rc = check_cuda(cudaSetDevice(s->device), "cudaSetDevice")) return rc;
     cudaError_t e = cudaSuccess;
-    for (int i = 0; i < K; ++i) {
-        cudaError_t ei = cudaStreamSynchronize(s->stream[i]);
+    for (int i = 0; i < s->n_slots; ++i) {
+        const cudaError_t ei = cudaStreamSynchronize(s->stream[i]);
         if (e == cudaSuccess) e = ei;
     }
-    cudaEventDestroy(meta_ready);
-    if (rc) return rc;
-    return check_cuda(e, "msda_host_forward_backward");
+    return check_cuda(e, "msda_host_wait");
+}
+
+int msda_host_forward_backward(msda_host_session *s, const void *value, const int64_t *spatial_shapes,
+                               const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                               const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                               void *grad_attn_weight, const msda_dims *dims, unsigned flags)
+{
+    const int rc = msda_host_submit(s, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                                    output, grad_value, grad_sampling_loc, grad_attn_weight, dims, flags);
+    const int rc_wait = msda_host_wait(s);  // drain even after a failed submit: earlier chunks may be in flight
+    return rc ? rc : rc_wait;
 }
 
 }  // extern "C"

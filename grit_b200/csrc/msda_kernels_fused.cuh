@@ -151,9 +151,9 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
 
     float part[3 * PPG];
     if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
-        bwd_row_body<T, CH, ACC, D, L, P, true>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, true>(accp, mine, vimg, gimg, MD, sW, g, go, part, 0u);
     else
-        bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part, 0u);
     group_reduce3<PPG, LPT>(part, sub);
 
     // after the reduction lane (g, sub) with sub % SPAN == 0 holds point pt: part[0] = d out/d attn,

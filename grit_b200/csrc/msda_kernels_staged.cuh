@@ -1,4 +1,4 @@
-// msda_kernels_v3.cuh -- persistent, shared-memory-staged kernels for large query counts (sm_100a).
+// msda_kernels_staged.cuh -- persistent, shared-memory-staged forward for large query counts (sm_100a).
 //
 // Why: the first two kernel generations are bound by the SM <-> L2 crossbar, not by HBM
 // (profiles/r01_*.txt): every bilinear tap is a 128-byte line that misses L1, and in the backward
@@ -18,7 +18,7 @@
 //   * rows are processed exactly like v2 (warp per row, resolve once, lane group per tap).
 #pragma once
 
-#include "msda_kernels_v2.cuh"
+#include "msda_common.cuh"
 
 namespace msda {
 
@@ -208,151 +208,6 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
                     for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
                 }
                 if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// backward
-// ------------------------------------------------------------------------------------------------
-// shared-memory fp32 accumulate of this lane's E channels of one tap.  Element order is rotated by the lane
-// group so the G groups of a warp hit disjoint bank sets (a tap is D consecutive floats = banks sub*E+j).
-template <int E>
-__device__ __forceinline__ void smem_add_chunk(float *p, const float (&go)[E], float s, int rot)
-{
-#pragma unroll
-    for (int j = 0; j < E; ++j) {
-        const int k = (j + rot) % E;
-        float x = 0.f;
-#pragma unroll
-        for (int e = 0; e < E; ++e) x = (e == k) ? go[e] : x;  // register select (no dynamic indexing)
-        atomicAdd(p + k, s * x);
-    }
-}
-
-template <typename T, int D, int L, int P, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-msda_bwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
-            const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
-            float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int N, int S,
-            int M, int Lq, int budget_elems)
-{
-    constexpr int E = Chunk<T>::E;
-    constexpr int LPT = D / E;
-    constexpr int G = 32 / LPT;
-    constexpr int LP = L * P;
-    constexpr int PPG = LP / G;
-    constexpr int WARPS = THREADS / 32;
-    static_assert(L <= kV3MaxLevels && LP <= 32 && 32 % LP == 0 && LP % G == 0, "unsupported");
-    static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *acc_s = reinterpret_cast<float *>(smem_raw);
-    __shared__ V3Plan plan;
-    plan_levels<L, D>(shapes, lsi, budget_elems, plan);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / LPT, sub = lane % LPT;
-    const int MD = M * D;
-    int lo, hi;
-    cta_slice(blockIdx.x, gridDim.x, M, Lq, lo, hi);
-    if (lo >= hi) return;
-    const int rp = lane % LP, rl = rp / P;
-    const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
-    const int staged4 = plan.staged_elems / 4;
-
-    for (int i = threadIdx.x; i < staged4; i += THREADS)
-        reinterpret_cast<float4 *>(acc_s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    for (int b = 0; b < N; ++b) {
-        for (int m = lo / Lq; m <= (hi - 1) / Lq; ++m) {
-            const int q0 = max(lo - m * Lq, 0), q1 = min(hi - m * Lq, Lq);
-            const int64_t img = ((int64_t)b * S * M + m) * D;
-            const T *vimg = value + img;
-            float *gimg = gv_acc + img;
-            __syncthreads();  // accumulators are zero (initial fill or previous flush)
-
-            for (int q = q0 + warp; q < q1; q += WARPS) {
-                const int64_t row = ((int64_t)b * Lq + q) * M + m;
-                const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + row * LP + rp);
-                const Resolved mine = resolve_point(xy.x, xy.y, rH, rW, rStart, attn + row * LP + rp);
-                float go[E];
-                Chunk<T>::load(grad_out + row * D + sub * E, go);
-                float part[3 * PPG];
-#pragma unroll
-                for (int it = 0; it < PPG; ++it) {
-                    const int pt = it * G + g;
-                    const int l = pt / P;
-                    const int pm = __shfl_sync(0xffffffffu, mine.pm, pt);
-                    const float a = __shfl_sync(0xffffffffu, mine.a, pt);
-                    const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
-                    const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
-                    const int W = plan.W[l];
-                    const int sb = plan.sbase[l];
-                    const int pix = pm >> 4;
-                    const int64_t o0 = (int64_t)pix * MD + sub * E, o1 = o0 + (int64_t)W * MD;
-                    float v0[E], v1[E], v2[E], v3[E];
-#pragma unroll
-                    for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
-                    if (pm & 1) Chunk<T>::load(vimg + o0, v0);
-                    if (pm & 2) Chunk<T>::load(vimg + o0 + MD, v1);
-                    if (pm & 4) Chunk<T>::load(vimg + o1, v2);
-                    if (pm & 8) Chunk<T>::load(vimg + o1 + MD, v3);
-                    const float hh = 1.f - lh, hw = 1.f - lw;
-                    const float ah = a * hh, al = a * lh;
-                    if (sb != kNotStaged) {
-                        float *s0 = acc_s + sb + pix * D + sub * E;
-                        float *s1 = s0 + W * D;
-                        if (pm & 1) smem_add_chunk<E>(s0, go, ah * hw, g);
-                        if (pm & 2) smem_add_chunk<E>(s0 + D, go, ah * lw, g);
-                        if (pm & 4) smem_add_chunk<E>(s1, go, al * hw, g);
-                        if (pm & 8) smem_add_chunk<E>(s1 + D, go, al * lw, g);
-                    } else {
-                        if (pm & 1) red_add_chunk<E>(gimg + o0, go, ah * hw);
-                        if (pm & 2) red_add_chunk<E>(gimg + o0 + MD, go, ah * lw);
-                        if (pm & 4) red_add_chunk<E>(gimg + o1, go, al * hw);
-                        if (pm & 8) red_add_chunk<E>(gimg + o1 + MD, go, al * lw);
-                    }
-                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        d0 = fmaf(go[e], v0[e], d0);
-                        d1 = fmaf(go[e], v1[e], d1);
-                        d2 = fmaf(go[e], v2[e], d2);
-                        d3 = fmaf(go[e], v3[e], d3);
-                    }
-                    part[3 * it + 0] = hh * (hw * d0 + lw * d1) + lh * (hw * d2 + lw * d3);
-                    part[3 * it + 1] = a * (hh * (d1 - d0) + lh * (d3 - d2));
-                    part[3 * it + 2] = a * (hw * (d2 - d0) + lw * (d3 - d1));
-                }
-                group_reduce3<PPG, LPT>(part, sub);
-                constexpr int SPAN = LPT / PPG;
-                if (sub % SPAN == 0) {
-                    const int pt = (sub / SPAN) * G + g;
-                    const int l = pt / P;
-                    reinterpret_cast<float2 *>(grad_loc)[row * LP + pt] =
-                        make_float2((float)plan.W[l] * part[1], (float)plan.H[l] * part[2]);
-                    grad_attn[row * LP + pt] = part[0];
-                }
-            }
-
-            // ---- flush the staged accumulators into grad_value and re-zero them ------------------------
-            __syncthreads();
-#pragma unroll
-            for (int l = 0; l < L; ++l) {
-                const int so = plan.soff[l];
-                if (so < 0) continue;
-                const int quads = plan.H[l] * plan.W[l] * (D / 4);
-                float *dst = gimg + (int64_t)plan.start[l] * MD;
-                for (int i = threadIdx.x; i < quads; i += THREADS) {
-                    const int pix = i / (D / 4), c4 = i % (D / 4);
-                    float4 *sp = reinterpret_cast<float4 *>(acc_s + so + pix * D) + c4;
-                    const float4 v = *sp;
-                    if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-                        red_add_f32x4(dst + (int64_t)pix * MD + c4 * 4, v.x, v.y, v.z, v.w);
-                    *sp = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
             }
         }
     }

@@ -13,7 +13,9 @@
 //     per-tap predicates, with predicated `red` issued from inline PTX so no branch is needed.
 #pragma once
 
-#include "msda_kernels_v2.cuh"
+#include "msda_common.cuh"
+#include "msda_kernels_generic.cuh"
+#include "msda_kernels_binned.cuh"
 
 namespace msda {
 
@@ -226,11 +228,11 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
 }
 
-template <typename T, typename CH, typename ACC, int D, int L, int P, bool ALL>
+template <typename T, typename CH, typename ACC, int D, int L, int P, bool ALL, bool SKIP = false>
 __device__ __forceinline__ void bwd_row_body(const ACC &accp, const Resolved &mine, const T *vimg,
                                              typename ACC::elem *gimg, int MD,
                                              const int (&sW)[L], int g, const float (&go)[CH::E],
-                                             float (&part)[3 * (L * P / (32 / (D / CH::E)))])
+                                             float (&part)[3 * (L * P / (32 / (D / CH::E)))], unsigned skipmask)
 {
     constexpr int E = CH::E;
     constexpr int G = 32 / (D / E);
@@ -248,10 +250,15 @@ __device__ __forceinline__ void bwd_row_body(const ACC &accp, const Resolved &mi
         load_taps<T, CH, ALL>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
         const float hh = 1.f - lh, hw = 1.f - lw;
         const float ah = a * hh, al = a * lh;
-        accp.template add<E, ALL>(gimg + o0, go, ah * hw, pm & 1);
-        accp.template add<E, ALL>(gimg + o1, go, ah * lw, pm & 2);
-        accp.template add<E, ALL>(gimg + o2, go, al * hw, pm & 4);
-        accp.template add<E, ALL>(gimg + o3, go, al * lw, pm & 8);
+        // levels in skipmask get their grad_value from msda_bwd_binned / msda_bwd_owned.  In every specialisation that
+        // has a SKIP instantiation the level of an iteration is the same for all lane groups (G divides P), so this is a
+        // warp-uniform branch around the reds and their multiplies, not a divergent one.
+        if (!SKIP || !((skipmask >> (pt / P)) & 1u)) {
+            accp.template add<E, ALL>(gimg + o0, go, ah * hw, pm & 1);
+            accp.template add<E, ALL>(gimg + o1, go, ah * lw, pm & 2);
+            accp.template add<E, ALL>(gimg + o2, go, al * hw, pm & 4);
+            accp.template add<E, ALL>(gimg + o3, go, al * lw, pm & 8);
+        }
         float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
@@ -294,12 +301,13 @@ __device__ __forceinline__ bool reduce_points(float (&part)[3 * PPG], int sub, i
     }
 }
 
-template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS>
+template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS, bool SKIP = false>
 __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))  // <= 64 registers: 32 resident warps per SM
 msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
             typename ACC::elem *__restrict__ gv_acc, const float *__restrict__ det_scale,
-            float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, unsigned rows_per_image)
+            float *__restrict__ grad_loc, float *__restrict__ grad_attn, int S, int M, unsigned rows_per_image,
+            int binned_budget)
 {
     constexpr int E = CH::E;
     constexpr int LPT = D / E;
@@ -334,11 +342,14 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     float go[E];
     CH::load(grad_out + row * D + sub * E, go);
 
+    // levels whose grad_value another kernel produces (same device-side rule as that kernel; 0 = none)
+    const unsigned skipmask = SKIP ? binned_level_mask<L>(sH, sW, D, binned_budget) : 0u;
+
     float part[3 * PPG];
     if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
-        bwd_row_body<T, CH, ACC, D, L, P, true>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, true, SKIP>(accp, mine, vimg, gimg, MD, sW, g, go, part, skipmask);
     else
-        bwd_row_body<T, CH, ACC, D, L, P, false>(accp, mine, vimg, gimg, MD, sW, g, go, part);
+        bwd_row_body<T, CH, ACC, D, L, P, false, SKIP>(accp, mine, vimg, gimg, MD, sW, g, go, part, skipmask);
 
     int it;
     float r3[3];

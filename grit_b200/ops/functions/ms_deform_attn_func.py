@@ -35,9 +35,19 @@ def set_deterministic(enabled: bool) -> bool:
     return prev
 
 
+_warned_fp64_det = False
+
+
 def _backward_flags(dtype) -> int:
-    if dtype != torch.float64 and (_deterministic or torch.are_deterministic_algorithms_enabled()):
-        return _lib.FLAG_DETERMINISTIC
+    global _warned_fp64_det
+    if _deterministic or torch.are_deterministic_algorithms_enabled():
+        if dtype != torch.float64:
+            return _lib.FLAG_DETERMINISTIC
+        if not _warned_fp64_det:  # int64 fixed point cannot carry fp64 precision: say so instead of silently ignoring it
+            _warned_fp64_det = True
+            import warnings
+            warnings.warn("grit_b200: the deterministic backward covers fp32 / bf16; fp64 grad_value is accumulated "
+                          "with floating-point atomics and is not bit-reproducible run to run")
     return 0
 
 
@@ -77,17 +87,21 @@ class MSDeformAttnFusedFunction(Function):
     """The core op with the module's pre-op arithmetic inside the kernels: takes the RAW outputs of
     the ``sampling_offsets`` / ``attention_weights`` Linears plus the reference points; softmax, ``offsets/normaliser +
     reference`` and the padding-mask fill (reference modules/ms_deform_attn.py:96-111) never touch HBM as separate
-    passes.  ``value`` is the value_proj output (N, S, M, D); when ``padding_mask`` is given its masked rows are zeroed
-    IN PLACE (and the same rows of grad_value in backward).  Not part of the reference API: ``MSDeformAttn`` uses it
-    when ``module.fused`` is on and ``_lib.fused_supported`` says yes."""
+    passes.  ``value`` is the value_proj output (N, S, M, D).  When ``padding_mask`` is given its masked rows are zeroed
+    IN PLACE (and the same rows of grad_value in backward); the tensor's autograd version counter is bumped, so any
+    other autograd node that saved ``value`` raises instead of silently reading modified data.  Pass a mask only for a
+    ``value`` you own -- ``MSDeformAttn`` does so for its own ``value_proj`` output and masks a caller-supplied
+    ``value=`` out of place.  Not part of the reference API: ``MSDeformAttn`` uses it when ``module.fused`` is on and
+    ``_lib.fused_supported`` says yes."""
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_offsets, attn_logits,
                 reference_points, padding_mask):
         if padding_mask is not None:
-            # raw in-place write (no autograd version bump): `value` is the value_proj output, whose producer
-            # (addmm) does not need its own output in backward; the matching rows of grad_value are zeroed below
+            # in-place write: `value` is the value_proj output, whose producer (addmm) does not need its own output
+            # in backward; the matching rows of grad_value are zeroed below
             _lib.mask_rows_(value, padding_mask)
+            torch.autograd.graph.increment_version(value)
         ctx.has_mask = padding_mask is not None
         sampling_offsets = sampling_offsets.contiguous()
         attn_logits = attn_logits.contiguous()

@@ -89,7 +89,8 @@ class MSDeformAttn(nn.Module):
         :param value                    optional (N, sum_l H_l*W_l, C): this layer's ``value_proj(input_flatten)`` computed
                                         elsewhere (see ``hoisted_value_proj``: GRIT's six decoder layers project the SAME
                                         memory, det_module.py:191-198, so one batched GEMM can serve all of them).  Not in
-                                        the reference signature; ``None`` gives the reference behaviour.
+                                        the reference signature; ``None`` gives the reference behaviour.  A supplied
+                                        tensor is never modified (the padding mask is applied to a copy).
         :return output                  (N, Length_{query}, C)
         """
         N, Len_q, _ = query.shape
@@ -97,27 +98,36 @@ class MSDeformAttn(nn.Module):
         if self.validate_shapes:
             assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
 
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(
+                reference_points.shape[-1]))
+        # In-place masking is only done on a tensor this module produced itself with a plain nn.Linear (addmm does not
+        # need its output in backward); a caller-supplied `value=` or a wrapped value_proj is masked out of place.
+        own_value = value is None and type(self.value_proj) is nn.Linear
         if value is None:
             value = self.value_proj(input_flatten)
+        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
+        attention_weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         if self.fused and query.is_cuda:
             # fused path: softmax, offsets/normaliser + reference points and the mask fill happen
-            # inside the gather kernels; falls through to the reference-shaped path when no specialisation exists
+            # inside the gather kernels; falls through to the reference-shaped path when no specialisation exists or
+            # the tensors are not laid out the way the kernels index them (_lib.fused_supported checks everything)
+            mask = input_padding_mask
+            if mask is not None and not own_value:
+                value, mask = value.masked_fill(mask[..., None], float(0)), None
             value4 = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-            offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-            if reference_points.shape[-1] not in (2, 4):
-                raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(
-                    reference_points.shape[-1]))
-            ref32 = reference_points.float()
-            if _lib.fused_supported(value4, offsets.float(), ref32):
-                logits = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+            ref32 = reference_points.float().expand(N, Len_q, self.n_levels, reference_points.shape[-1]).contiguous()
+            offs32, logits32 = sampling_offsets.float().contiguous(), attention_weights.float().contiguous()
+            if _lib.fused_supported(value4, input_spatial_shapes, input_level_start_index, offs32, logits32, ref32,
+                                    mask):
                 output = MSDeformAttnFusedFunction.apply(value4, input_spatial_shapes, input_level_start_index,
-                                                         offsets.float(), logits.float(), ref32, input_padding_mask)
+                                                         offs32, logits32, ref32, mask)
                 return self.output_proj(output)
+            if mask is None:
+                input_padding_mask = None  # already applied above
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        sampling_offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-        attention_weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
 
         if reference_points.shape[-1] == 2:
@@ -127,9 +137,6 @@ class MSDeformAttn(nn.Module):
         elif reference_points.shape[-1] == 4:
             sampling_locations = reference_points[:, :, None, :, None, :2] \
                 + sampling_offsets / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
-        else:
-            raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(
-                reference_points.shape[-1]))
         output = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index, sampling_locations,
                                             attention_weights, self.im2col_step)
         return self.output_proj(output)

@@ -62,7 +62,10 @@ enum {
     MSDA_FLAG_ZERO_GRAD_VALUE = 1u << 0, /* backward: memset grad_value on the stream before accumulating   */
     MSDA_FLAG_DETERMINISTIC = 1u << 1,   /* backward (f32/bf16): bit-reproducible grad_value -- int64 fixed-point   */
                                          /* accumulation with integer atomics; needs the workspace                  */
-    MSDA_FLAG_FORCE_GENERIC = 1u << 2    /* testing: skip the specialised kernels, use the generic ones     */
+    MSDA_FLAG_FORCE_GENERIC = 1u << 2,   /* testing: skip the specialised kernels, use the generic ones     */
+    MSDA_FLAG_ALIGNED16 = 1u << 3        /* msda_backward_workspace_bytes only: the caller guarantees that every    */
+                                         /* tensor it will pass is 16-byte aligned (lets bf16 report 0 bytes when   */
+                                         /* the owned backward, which needs no fp32 image, will run)                */
 };
 
 /* Problem geometry.  All counts are element counts, not bytes. */
@@ -88,13 +91,16 @@ const char *msda_last_kernel(void);
 /* Kernel launches enqueued by this thread since the counter was last reset (memsets excluded). */
 int64_t msda_launch_count(int reset);
 
-/* Tuning / A-B testing knob (process-wide).  Keys:
- *   "variant"     1 first-generation kernels | 2 resolve-once kernels | 3 persistent shared-memory-staged kernels |
- *                 4 persistent forward with software prefetch | 5 lean resolve-once kernels (default) |
- *                 0 choose 3 or 2 by problem size
- *   "hoist"       0 | 1   (variant 5 forward: issue all tap loads of a row before the first FMA)
- *   "head_major"  0 | 1   (variant 2: row order)        "warps"  4 | 8 | 16  (variant 2/4: warps per CTA, D=32 L=P=4)
- *   "v3_threads"  512 | 1024                             "v3_min_rows"  threshold of the size heuristic
+/* Tuning / A-B testing knob (process-wide; for benchmarks and tests).  Keys:
+ *   "variant"        forward: 5 lean row kernel (default) | 3 persistent shared-memory-staged forward
+ *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
+ *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
+ *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
+ *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
+ *                    2 row kernel + on-SM aggregation of the coarse levels (msda_bwd_binned) |
+ *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems)
+ *   "bin_min_rows"   auto rule: mode 2 when num_query >= this      (default 1024)
+ *   "owned_max_taps" auto rule: mode 3 when num_query*L*P*4 <= this * spatial_size   (default 4)
  * Returns the previous value, or -1 for an unknown key.  Results do not depend on the knobs beyond fp rounding. */
 int msda_set_tuning(const char *key, int value);
 
@@ -104,7 +110,8 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
                  int dtype, unsigned flags, void *cuda_stream);
 
 /* Bytes of device scratch msda_backward needs for this problem: 0 for f32/f64; N*S*M*D*4 for bf16 (fp32 image of
- * grad_value); N*S*M*D*8 + 16 with MSDA_FLAG_DETERMINISTIC.  The workspace must be 16-byte aligned. */
+ * grad_value; 0 with MSDA_FLAG_ALIGNED16 when the owned backward applies); N*S*M*D*8 + 16 with
+ * MSDA_FLAG_DETERMINISTIC.  The workspace must be 16-byte aligned. */
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags);
 
 /* grad_value += scatter(w*attn*grad_out); grad_sampling_loc, grad_attn_weight = analytic gradients. */
@@ -163,13 +170,21 @@ int msda_probe_ceiling(int which, void *scratch, size_t scratch_bytes, int64_t *
  * the inputs host->device image-chunk by image-chunk, runs forward+backward, and copies the four
  * results back, overlapping copies with kernels.  Host buffers should be page-locked for full
  * PCIe bandwidth.  spatial_shapes / level_start_index are HOST pointers here.
- * The call returns after all results have landed in the host buffers.
+ * msda_host_forward_backward returns after all results have landed in the host buffers.  msda_host_submit enqueues
+ * the same work and returns at once, so consecutive calls (the six layers of a decoder, the next batch) keep the
+ * copy / kernel / copy pipeline full across call boundaries; msda_host_wait blocks until everything submitted so far
+ * has landed.  Host buffers handed to msda_host_submit must stay valid and untouched until msda_host_wait returns.
  */
 typedef struct msda_host_session msda_host_session;
 
 int msda_host_session_create(msda_host_session **session, const msda_dims *max_dims, int dtype, int device,
                              int images_per_chunk);
 void msda_host_session_destroy(msda_host_session *session);
+int msda_host_submit(msda_host_session *session, const void *value, const int64_t *spatial_shapes,
+                     const int64_t *level_start_index, const void *sampling_loc, const void *attn_weight,
+                     const void *grad_output, void *output, void *grad_value, void *grad_sampling_loc,
+                     void *grad_attn_weight, const msda_dims *dims, unsigned flags);
+int msda_host_wait(msda_host_session *session);
 int msda_host_forward_backward(msda_host_session *session, const void *value, const int64_t *spatial_shapes,
                                const int64_t *level_start_index, const void *sampling_loc,
                                const void *attn_weight, const void *grad_output, void *output,

@@ -1,0 +1,98 @@
+"""GPU: element-wise parity at the FULL sizes of BASELINE.json's configs, through the C ABI with the
+default (auto) kernel selection -- so the shapes the bench measures are the shapes that are checked:
+
+  config 3  encoder 800x1333, Lq = S = 22223, D = 32     -> fwd_v5, bwd_v5 + msda_bwd_binned (levels 2, 3 on chip)
+  config 2  encoder 384x640,  Lq = S = 5100,  D = 32     -> same kernels, three binned levels
+  config 4  decoder Lq = 150, D = 64, S = 22223 / 5100   -> fwd_v5, bwd_v5 + msda_bwd_owned
+
+in fp32 and bf16, with uniform and detector-like sampling locations and a padding mask on the right/bottom 10 % of every
+level.  N = 2 images: the OpenMP C oracle needs about a second per image at these sizes.  Tolerances as everywhere
+(tests/test_gpu_parity.py: fp32 1e-5 forward / 1e-4 gradients, bf16 2e-2).
+"""
+import numpy as np
+import pytest
+import torch
+
+from . import helpers
+from .test_gpu_parity import assert_parity, lib, oracle_results, run_kernels  # noqa: F401  (lib is a fixture)
+
+pytestmark = pytest.mark.gpu
+
+
+def detector_like_loc(rng, N, Lq, M, shapes, P, encoder):
+    """reference point = own pixel centre (encoder) or U[0,1) (decoder); offsets = the
+    module-init ring pattern (p+1) * unit_dir(head) (reference modules/ms_deform_attn.py:58-63) + N(0, 2 px), divided
+    by (W_l, H_l) (reference :106-108)."""
+    L = len(shapes)
+    if encoder:
+        refs = []
+        for h, w in shapes:
+            ys, xs = np.meshgrid(np.arange(h) + 0.5, np.arange(w) + 0.5, indexing="ij")
+            refs.append(np.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
+        ref = np.broadcast_to(np.concatenate(refs, 0)[None], (N, Lq, 2))
+    else:
+        ref = rng.random((N, Lq, 2))
+    ang = np.arange(M) * (2.0 * np.pi / M)
+    ring = np.stack([np.cos(ang), np.sin(ang)], -1)
+    ring = ring / np.abs(ring).max(-1, keepdims=True)
+    offs = ring.reshape(1, 1, M, 1, 1, 2) * np.arange(1, P + 1).reshape(1, 1, 1, 1, P, 1)
+    offs = offs + 2.0 * rng.standard_normal((N, Lq, M, L, P, 2))
+    norm = np.asarray([[w, h] for h, w in shapes], dtype=np.float64).reshape(1, 1, 1, L, 1, 2)
+    return ref.reshape(N, Lq, 1, 1, 1, 2) + offs / norm
+
+
+def padding_mask(N, shapes, frac=0.1):
+    """True on the right / bottom `frac` of every level (padding-mask variant)."""
+    parts = []
+    for h, w in shapes:
+        m = np.zeros((h, w), dtype=bool)
+        m[int(round(h * (1 - frac))):, :] = True
+        m[:, int(round(w * (1 - frac))):] = True
+        parts.append(m.reshape(-1))
+    return np.broadcast_to(np.concatenate(parts)[None], (N, sum(h * w for h, w in shapes))).copy()
+
+
+FULL_SIZE = [
+    # id,                 pyramid,                   Lq,   D,  expected backward kernel substring
+    ("enc800x1333_d32", helpers.PYRAMID_800x1333, None, 32, "+binned"),
+    ("enc384x640_d32", helpers.PYRAMID_384x640, None, 32, "+binned"),
+    ("dec800x1333_d64", helpers.PYRAMID_800x1333, 150, 64, "+owned"),
+    ("dec384x640_d64", helpers.PYRAMID_384x640, 150, 64, "+owned"),
+    ("dec800x1333_d32", helpers.PYRAMID_800x1333, 150, 32, "+owned"),
+]
+
+
+@pytest.mark.parametrize("dist", ["uniform", "detector"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name,shapes,Lq,D,bsub", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_elementwise_vs_oracle(lib, oracle, name, shapes, Lq, D, bsub, dtype, dist):
+    N, M, P = 2, 8, 4
+    S = sum(h * w for h, w in shapes)
+    encoder = Lq is None
+    Lq = Lq or S
+    case = helpers.make_inputs(N, Lq, M, D, shapes, P, seed=len(name) + D, dtype=np.float32)
+    rng = np.random.default_rng(7)
+    if dist == "detector":
+        case["loc"] = detector_like_loc(rng, N, Lq, M, shapes, P, encoder).astype(np.float32)
+    # masked pixels are zero rows of value (reference modules/ms_deform_attn.py:96-97)
+    case["value"][padding_mask(N, shapes)] = 0.0
+    case = helpers.rounded_case(case, dtype)
+    got = run_kernels(lib, case, dtype)
+    assert got["fwd_kernel"].startswith("fwd_v5"), got["fwd_kernel"]
+    assert bsub in got["bwd_kernel"], got["bwd_kernel"]
+    assert_parity(got, oracle_results(oracle, case), case, dtype, f"{name} {dist}")
+
+
+def test_full_size_backward_strategies_agree(lib):
+    """800x1333 encoder shape, fp32: the row-only backward and the row + binned backward produce the same grad_value up
+    to fp32 summation order, and bit-identical grad_sampling_loc / grad_attn_weight (same row kernel)."""
+    from .test_gpu_parity import run_backward_mode
+    from .conftest import max_norm_err
+    shapes = helpers.PYRAMID_800x1333
+    S = sum(h * w for h, w in shapes)
+    case = helpers.make_inputs(2, S, 8, 32, shapes, 4, seed=11, dtype=np.float32)
+    row = run_backward_mode(lib, case, torch.float32, "row")
+    binned = run_backward_mode(lib, case, torch.float32, "binned")
+    assert "+binned" in binned["bwd_kernel"] and "+binned" not in row["bwd_kernel"]
+    assert torch.equal(row["grad_loc"], binned["grad_loc"]) and torch.equal(row["grad_attn"], binned["grad_attn"])
+    assert max_norm_err(binned["grad_value"].double().cpu().numpy(), row["grad_value"].double().cpu().numpy()) < 2e-5

@@ -157,24 +157,21 @@ def test_specialised_and_generic_kernels_agree(lib, oracle, dtype):
     assert_parity(slow, ref, case, dtype, "generic")
 
 
-KERNEL_GENERATIONS = [  # (msda_set_tuning settings, expected kernel-name prefix)
-    ({"variant": 1}, "vec"),
-    ({"variant": 2, "head_major": 0, "warps": 4}, "v2"),
-    ({"variant": 2, "head_major": 1, "warps": 8}, "v2"),
-    ({"variant": 2, "head_major": 0, "warps": 16}, "v2"),
-    ({"variant": 3, "v3_threads": 512}, "v3"),
-    ({"variant": 3, "v3_threads": 1024}, "v3"),
-    ({"variant": 4, "warps": 8}, "v2"),
-    ({"variant": 5, "warps": 4, "hoist": 0}, "v5"),
-    ({"variant": 5, "warps": 8, "hoist": 1}, "v5"),
+KERNEL_VARIANTS = [  # (msda_set_tuning settings, expected forward-kernel prefix, expected backward-kernel substring)
+    ({"variant": 5, "warps": 4, "hoist": 0, "bwd_mode": 1}, "fwd_v5", "bwd_v5<"),
+    ({"variant": 5, "warps": 8, "hoist": 1, "bwd_mode": 1}, "fwd_v5", "bwd_v5<"),
+    ({"variant": 3, "v3_threads": 512, "bwd_mode": 2}, "fwd_staged", "+binned"),
+    ({"variant": 3, "v3_threads": 1024, "bwd_mode": 3}, "fwd_staged", "+owned"),
+    ({"variant": 3, "v3_threads": 768, "bwd_mode": 0}, "fwd_staged", "bwd_v5"),
 ]
 
 
-@pytest.mark.parametrize("tuning,prefix", KERNEL_GENERATIONS, ids=lambda t: str(t))
+@pytest.mark.parametrize("tuning,fprefix,bsub", KERNEL_VARIANTS, ids=lambda t: str(t))
 @pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 64), (torch.bfloat16, 32), (torch.bfloat16, 64)])
-def test_every_kernel_generation_matches_oracle(lib, oracle, tuning, prefix, dtype, D):
-    """All selectable kernel generations (A/B knobs of include/msda.h) compute the same function.  The pyramid is
-    big enough that the shared-memory-staged generation stages some levels and leaves others in global memory."""
+def test_every_kernel_variant_matches_oracle(lib, oracle, tuning, fprefix, bsub, dtype, D):
+    """All selectable kernel variants (A/B knobs of include/msda.h) compute the same function: the row kernels, the
+    shared-memory-staged forward, and the three backward strategies (row reds, row + binned coarse levels, owned).
+    The pyramid is big enough that the staged / binned paths keep some levels on chip and leave others in global memory."""
     shapes = [(40, 60), (20, 30), (10, 15), (5, 8)]
     case = helpers.rounded_case(helpers.make_inputs(2, 301, 8, D, shapes, 4, seed=17, lo=-0.1, hi=1.1), dtype)
     saved = {k: lib.set_tuning(k, v) for k, v in tuning.items()}
@@ -183,8 +180,91 @@ def test_every_kernel_generation_matches_oracle(lib, oracle, tuning, prefix, dty
     finally:
         for k, v in saved.items():
             lib.set_tuning(k, v)
-    assert prefix in got["bwd_kernel"], got["bwd_kernel"]
+    assert got["fwd_kernel"].startswith(fprefix), got["fwd_kernel"]
+    assert bsub in got["bwd_kernel"], got["bwd_kernel"]
     assert_parity(got, oracle_results(oracle, case), case, dtype, str(tuning))
+
+
+BWD_MODES = {"row": 1, "binned": 2, "owned": 3}
+
+
+def run_backward_mode(lib, case, dtype, mode, accumulate_into=None):
+    """Backward through the C ABI with a forced strategy; returns torch tensors + the kernel name."""
+    import ctypes
+    t = helpers.to_cuda(case, dtype)
+    n, s, m, d = t["value"].shape
+    _, lq, _, l, p, _ = t["loc"].shape
+    prev = lib.set_tuning("bwd_mode", BWD_MODES[mode])
+    try:
+        if accumulate_into is None:
+            gv, gl, ga = lib.backward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"],
+                                      t["grad_out"].view(n, lq, m * d))
+        else:  # raw call without FLAG_ZERO_GRAD_VALUE: grad_value is accumulated into
+            raw = lib.load()
+            dims = lib.MsdaDims(n, s, m, d, l, lq, p)
+            gv = accumulate_into.clone()
+            gl, ga = torch.empty_like(t["loc"]), torch.empty_like(t["attn"])
+            code = lib._DTYPE_CODE[dtype]
+            wsb = raw.msda_backward_workspace_bytes(ctypes.byref(dims), code, 0)
+            ws = torch.empty(max(wsb // 4, 4), dtype=torch.float32, device="cuda")
+            rc = raw.msda_backward(lib._ptr(t["value"]), lib._ptr(t["shapes"]), lib._ptr(t["level_start"]),
+                                   lib._ptr(t["loc"]), lib._ptr(t["attn"]), lib._ptr(t["grad_out"]), lib._ptr(gv),
+                                   lib._ptr(gl), lib._ptr(ga), ctypes.byref(dims), code, 0, lib._ptr(ws), wsb,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            assert rc == 0, raw.msda_last_error()
+        name = lib.last_kernel()
+        torch.cuda.synchronize()
+    finally:
+        lib.set_tuning("bwd_mode", prev)
+    return dict(grad_value=gv, grad_loc=gl, grad_attn=ga, bwd_kernel=name)
+
+
+@pytest.mark.parametrize("mode", ["binned", "owned"])
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 64), (torch.bfloat16, 32), (torch.bfloat16, 64)])
+@pytest.mark.parametrize("shapes,Lq", [
+    ([(40, 60), (20, 30), (10, 15), (5, 8)], 1300),   # several query tiles per item, every level class
+    ([(33, 35), (1, 9), (7, 1), (2, 2)], 257),        # 1-pixel-wide / 1-pixel-high levels: every bin is a border bin
+    ([(64, 64), (3, 3), (1, 1), (40, 40)], 70),       # levels out of size order, fewer rows than one tile
+])
+def test_aggregating_backward_strategies_vs_oracle(lib, oracle, mode, dtype, D, shapes, Lq):
+    """msda_bwd_binned (coarse levels aggregated in shared memory, four colour phases) and msda_bwd_owned (counting
+    sort by pixel, every grad_value line stored once) against the fp64 oracle, incl. out-of-range samples."""
+    case = helpers.rounded_case(helpers.make_inputs(3, Lq, 8, D, shapes, 4, seed=31 + Lq, lo=-0.3, hi=1.3), dtype)
+    got = run_backward_mode(lib, case, dtype, mode)
+    assert ("+" + mode) in got["bwd_kernel"], got["bwd_kernel"]
+    ref = oracle_results(oracle, case)
+    _, gtol = TOL[dtype]
+    assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref["grad_value"]) <= gtol
+    assert max_norm_err(got["grad_attn"].double().cpu().numpy(), ref["grad_attn"]) <= gtol
+    # the strategies share the row kernel for grad_loc / grad_attn: bit-identical to the plain row backward
+    row = run_backward_mode(lib, case, dtype, "row")
+    assert torch.equal(row["grad_loc"], got["grad_loc"]) and torch.equal(row["grad_attn"], got["grad_attn"])
+    assert max_norm_err(got["grad_value"].double().cpu().numpy(), row["grad_value"].double().cpu().numpy()) <= gtol
+
+
+@pytest.mark.parametrize("mode", ["binned", "owned"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_aggregating_backward_accumulates_into_grad_value(lib, oracle, mode, dtype):
+    """Without MSDA_FLAG_ZERO_GRAD_VALUE the backward adds to what grad_value holds (include/msda.h), whichever strategy."""
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    case = helpers.rounded_case(helpers.make_inputs(2, 300, 8, 32, shapes, 4, seed=3), dtype)
+    t = helpers.to_cuda(case, dtype)
+    base = torch.randn_like(t["value"])
+    got = run_backward_mode(lib, case, dtype, mode, accumulate_into=base)
+    ref = oracle_results(oracle, case)["grad_value"] + base.double().cpu().numpy()
+    assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref) <= TOL[dtype][1]
+
+
+def test_nonfinite_gradients_propagate_through_aggregating_strategies(lib):
+    """0 * inf and NaN in grad_output reach grad_value as NaN under every strategy (no silent zeroing)."""
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    case = helpers.make_inputs(1, 64, 8, 32, shapes, 4, seed=4, dtype=np.float32)
+    case["grad_out"][0, 5, :32] = np.nan
+    for mode in ("row", "binned", "owned"):
+        got = run_backward_mode(lib, case, torch.float32, mode)
+        gv = got["grad_value"][0, :, 0]
+        assert torch.isnan(gv).any(), mode
+        assert torch.isfinite(got["grad_value"][0, :, 1:]).all(), mode
 
 
 @pytest.mark.parametrize("dtype,D,shapes,P", [
@@ -261,13 +341,13 @@ def test_edge_cases(lib, oracle):
 
 
 def test_fallback_paths_large_batch_and_misaligned_storage(lib, oracle):
-    """Dispatch corner cases: batch > 65535 (beyond gridDim.y of the default kernels) and tensors whose storage is not
-    16-byte aligned must still give oracle results (older generation / generic kernels take over)."""
+    """Dispatch corner cases: batch > 65535 (beyond gridDim.y of the row kernels) and tensors whose storage is not
+    16-byte aligned must still give oracle results (the generic kernels take over)."""
     # 1) 70 000 tiny images
     N = 70000
     case = helpers.make_inputs(N, 1, 1, 32, [(2, 2)], 4, seed=2, dtype=np.float32)
     got = run_kernels(lib, case, torch.float32)
-    assert "v5" not in got["fwd_kernel"] and is_specialised(got["fwd_kernel"]), got["fwd_kernel"]
+    assert not is_specialised(got["fwd_kernel"]) and not is_specialised(got["bwd_kernel"]), got["fwd_kernel"]
     case64 = helpers.rounded_case(case, torch.float32)
     assert_parity(got, oracle_results(oracle, case64), case64, torch.float32, "large batch")
     # 2) value / grad_out views that start 4 bytes into their storage
@@ -687,3 +767,142 @@ def test_host_session_matches_device_path(lib, oracle):
     assert max_norm_err(out.numpy(), ref["out"]) < 1e-5
     assert max_norm_err(gv.numpy(), ref["grad_value"]) < 1e-4
     assert max_norm_err(ga.numpy(), ref["grad_attn"]) < 1e-4
+
+
+# ---- round-2 additions: fused + deterministic, ownership of `value=`, fused-path validation, the reference's own test.py ----
+
+def _small_module_problem(D=32, N=2, Lq=120, seed=2):
+    from grit_b200 import MSDeformAttn
+    torch.manual_seed(seed)
+    M, L, P = 8, 4, 4
+    C = M * D
+    shapes_l = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes_l)
+    mod = MSDeformAttn(C, L, M, P).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.2)
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.from_numpy(helpers.level_start(shapes_l)).cuda()
+    query = torch.randn(N, Lq, C, device="cuda")
+    src = torch.randn(N, S, C, device="cuda")
+    ref = torch.rand(N, Lq, L, 2, device="cuda")
+    mask = torch.zeros(N, S, dtype=torch.bool, device="cuda")
+    mask[:, ::7] = True
+    gout = torch.randn(N, Lq, C, device="cuda")
+    return mod, query, src, ref, shapes, lsi, mask, gout
+
+
+@pytest.mark.parametrize("D", [32, 64])
+def test_fused_deterministic_module_is_bit_reproducible_and_matches_fp64(lib, D):
+    """MSDeformAttn on its default fused path with the deterministic switch on (msda_bwd_fused<..., AccFix64>): three
+    runs give identical bits for every gradient that depends on grad_value, and the result matches the same module run
+    unfused in fp64 (generic kernels)."""
+    import copy
+
+    import grit_b200
+    mod, query, src, ref, shapes, lsi, mask, gout = _small_module_problem(D)
+    mod.validate_shapes = False
+    prev = grit_b200.set_deterministic(True)
+    try:
+        runs = []
+        for _ in range(3):
+            mod.zero_grad(set_to_none=True)
+            s = src.clone().requires_grad_(True)
+            q = query.clone().requires_grad_(True)
+            out = mod(q, ref, s, shapes, lsi, mask)
+            kernel_fwd = lib.last_kernel()
+            kernel_bwd = []
+
+            def note_kernel(grad):  # msda_last_kernel is thread-local: read it on the autograd thread that ran the op
+                kernel_bwd.append(lib.last_kernel())
+                return grad
+            s.register_hook(note_kernel)
+            out.backward(gout)
+            kernel_bwd = kernel_bwd[0]
+            runs.append(dict(out=out.detach().clone(), src=s.grad.clone(), q=q.grad.clone(),
+                             vw=mod.value_proj.weight.grad.clone(), vb=mod.value_proj.bias.grad.clone()))
+        assert kernel_fwd.startswith("fwd_fused") and "bwd_fused" in kernel_bwd and "deterministic" in kernel_bwd, \
+            (kernel_fwd, kernel_bwd)
+        for r in runs[1:]:
+            for k in r:
+                assert torch.equal(r[k], runs[0][k]), k
+    finally:
+        grit_b200.set_deterministic(prev)
+    ref_mod = copy.deepcopy(mod).double()
+    ref_mod.fused = False
+    ref_mod.zero_grad(set_to_none=True)
+    s64 = src.double().requires_grad_(True)
+    q64 = query.double().requires_grad_(True)
+    out64 = ref_mod(q64, ref.double(), s64, shapes, lsi, mask)
+    out64.backward(gout.double())
+    assert max_norm_err(runs[0]["out"].cpu().numpy(), out64.detach().cpu().numpy()) < 2e-4
+    assert max_norm_err(runs[0]["src"].cpu().numpy(), s64.grad.cpu().numpy()) < 2e-4
+    assert max_norm_err(runs[0]["q"].cpu().numpy(), q64.grad.cpu().numpy()) < 2e-4
+    assert max_norm_err(runs[0]["vw"].cpu().numpy(), ref_mod.value_proj.weight.grad.cpu().numpy()) < 2e-4
+
+
+def test_module_never_modifies_a_caller_supplied_value(lib):
+    """`value=` (hoisted value_proj) with a padding mask: the supplied tensor keeps its bits, results equal the
+    module projecting for itself, gradients reach the supplied tensor with zero rows where the mask is set."""
+    mod, query, src, ref, shapes, lsi, mask, gout = _small_module_problem()
+    mod.validate_shapes = False
+    own = mod(query, ref, src, shapes, lsi, mask)
+    value = mod.value_proj(src).detach().clone().requires_grad_(True)
+    before = value.detach().clone()
+    out = mod(query, ref, src, shapes, lsi, mask, value=value)
+    assert torch.equal(value.detach(), before)
+    assert torch.equal(out, own)
+    out.backward(gout)
+    assert torch.count_nonzero(value.grad[mask]) == 0 and torch.count_nonzero(value.grad[~mask]) > 0
+
+
+def test_fused_path_validates_layouts_and_falls_back(lib):
+    """the fused entry points check dtypes / shapes / devices / alignment like _check_inputs does; the module
+    falls back to the reference-shaped path instead of handing mis-typed tensors to pointer arithmetic."""
+    mod, query, src, ref, shapes, lsi, mask, gout = _small_module_problem()
+    mod.validate_shapes = False
+    good = mod(query, ref, src, shapes, lsi, mask)
+    assert lib.last_kernel().startswith("fwd_fused")
+    # a reference-point tensor that broadcasts over levels is legal in the reference (modules/ms_deform_attn.py:106)
+    ref1 = ref[:, :, :1].contiguous()
+    out = mod(query, ref1, src, shapes, lsi, mask)
+    assert lib.last_kernel().startswith("fwd_fused")
+    assert torch.allclose(out, mod(query, ref1.expand(-1, -1, 4, -1).contiguous(), src, shapes, lsi, mask))
+    n, s = src.shape[:2]
+    value4 = mod.value_proj(src).view(n, s, 8, 32)
+    offs = torch.zeros(n, query.shape[1], 8, 4, 4, 2, device="cuda")
+    logits = torch.zeros(n, query.shape[1], 8, 16, device="cuda")
+    assert lib.fused_supported(value4, shapes, lsi, offs, logits, ref, mask)
+    assert not lib.fused_supported(value4, shapes.int(), lsi, offs, logits, ref, mask)            # int32 shapes
+    assert not lib.fused_supported(value4, shapes, lsi, offs, logits.double(), ref, mask)          # fp64 logits
+    assert not lib.fused_supported(value4, shapes, lsi, offs, logits, ref1, mask)                  # (N,Lq,1,2) ref
+    assert not lib.fused_supported(value4, shapes, lsi, offs, logits, ref, mask[:, :-1].contiguous())  # mask shape
+    assert not lib.fused_supported(value4, shapes, lsi, offs, logits, ref, mask.cpu())             # mask device
+    with pytest.raises(RuntimeError):
+        lib.fused_forward(value4, shapes.int(), lsi, offs, logits, ref)
+    assert torch.isfinite(good).all()
+
+
+def test_reference_test_py_runs_unchanged(lib, tmp_path):
+    """the reference's own models/ops/test.py (and its own functions/ms_deform_attn_func.py) executed
+    UNCHANGED on top of this library: `import MultiScaleDeformableAttention` resolves to the C-ABI shim
+    (grit_b200.install_as_reference_ops).  The files are copied into git-ignored baseline/_ref/ops_test by
+    __graft_entry__.build() in the build container (they are not part of this repo); every flag the script prints
+    (test.py:40,56,76) must be True."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ops_dir = os.path.join(root, "baseline", "_ref", "ops_test")
+    if not os.path.exists(os.path.join(ops_dir, "test.py")):
+        pytest.skip("baseline/_ref/ops_test/test.py is absent (the reference tree was not available to build())")
+    code = ("import sys, runpy; sys.path.insert(0, %r); import grit_b200; "
+            "grit_b200.install_as_reference_ops(alias_models_ops=False); sys.path.insert(0, %r); "
+            "runpy.run_path(%r, run_name='__main__')" % (root, ops_dir, os.path.join(ops_dir, "test.py")))
+    proc = subprocess.run([sys.executable, "-c", code], cwd=ops_dir, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("* ")]
+    assert len(lines) == 6, proc.stdout  # 2 forward checks + gradcheck for D in {30, 32, 64, 71}
+    for ln in lines:
+        assert ln.startswith("* True"), ln
