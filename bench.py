@@ -312,7 +312,8 @@ def main():
     import torch.distributed as dist
     from grit_b200 import _lib
 
-    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("MSDA_BENCH_NUMA_BIND", "0") == "1" \
+    # multi-rank: bind each rank (and so its first-touch pinned buffers) to its GPU's NUMA node unless told not to
+    numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("MSDA_BENCH_NUMA_BIND", "1") == "1" \
         else None
     lib = _lib.load()  # raises if the CUDA library is missing: no fallback
     if not torch.cuda.is_available():
@@ -349,8 +350,39 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     P_ = _lib._ptr
     d_model = M * D
-    grad_bucket = torch.zeros(layers * OP_PARAMS_PER_LAYER.get(d_model, 4 * d_model * d_model), device=device) \
-        if world > 1 else None
+    n_bucket = layers * OP_PARAMS_PER_LAYER.get(d_model, 4 * d_model * d_model)
+    grad_bucket = torch.zeros(n_bucket, device=device) if world > 1 else None
+    # what each rank contributes to the all-reduce: a rank-dependent, non-zero pattern whose sum over ranks is known
+    grad_src = ((torch.arange(n_bucket, device=device) % 251).float() * 1e-3 + 1.0) * (rank + 1) if world > 1 else None
+
+    def multi_gpu_selfcheck():
+        """Untimed, world > 1: (1) every rank runs ONE layer on identical inputs (shared seed) with the deterministic
+        backward; bit-level checksums of all four results are all-gathered and must be equal on every rank -- the
+        replicas compute the same function.  (2) the bucket all-reduce of a non-zero rank-dependent pattern must equal
+        the closed-form sum."""
+        chk_cfg = dict(cfg, N=min(N, 2))
+        x = make_layer_inputs(torch, chk_cfg, device, 424242, args.loc_dist)  # same seed on every rank
+        o = _lib.forward(x["value"], shapes, lsi, x["loc"], x["attn"])
+        g3 = _lib.backward(x["value"], shapes, lsi, x["loc"], x["attn"], x["gout"], _lib.FLAG_DETERMINISTIC)
+
+        def digest(t):
+            bits = t.contiguous().view(torch.int16 if t.element_size() == 2 else torch.int32)
+            return bits.to(torch.int64).sum()
+        mine = torch.stack([digest(t) for t in (o,) + tuple(g3)])
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        same = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+        grad_bucket.copy_(grad_src)
+        dist.all_reduce(grad_bucket)
+        expect = grad_src / (rank + 1) * (world * (world + 1) / 2)
+        sum_ok = bool(torch.allclose(grad_bucket, expect, rtol=1e-6, atol=0))
+        if not same or not sum_ok:
+            raise RuntimeError(f"multi-GPU self-check failed on rank {rank}: ranks_bit_identical={same}, "
+                               f"allreduce_sum_ok={sum_ok}")
+        return {"ranks_bit_identical": same, "allreduce_sum_ok": sum_ok,
+                "what": "one layer on identical inputs per rank, deterministic backward, int checksums of out/grad_value/"
+                        "grad_loc/grad_attn all-gathered and compared; bucket all-reduce of a rank-dependent pattern "
+                        "checked against its closed form"}
 
     def fwd(s):
         rc = lib.msda_forward(P_(s["value"]), P_(shapes), P_(lsi), P_(s["loc"]), P_(s["attn"]), P_(out),
@@ -358,8 +390,12 @@ def main():
         if rc:
             raise RuntimeError(lib.msda_last_error().decode())
 
+    # strategy 3 (owned) writes every grad_value line once and needs no zero-fill; the others accumulate into a zeroed
+    # grad_value (fp32: zero_() inside the step, outside the kernel bracket, as in round 1; bf16: the library's workspace)
+    owned = lib.msda_backward_strategy(ctypes.byref(dims), code, 0) == 3
+
     def bwd(s):
-        flags = _lib.FLAG_ZERO_GRAD_VALUE if dt == torch.bfloat16 else 0
+        flags = _lib.FLAG_ZERO_GRAD_VALUE if (dt == torch.bfloat16 or owned) else 0
         rc = lib.msda_backward(P_(s["value"]), P_(shapes), P_(lsi), P_(s["loc"]), P_(s["attn"]), P_(s["gout"]),
                                P_(gv), P_(gl), P_(ga), ctypes.byref(dims), code, flags, P_(ws), ws_bytes,
                                ctypes.c_void_p(stream))
@@ -378,7 +414,7 @@ def main():
             if record:
                 e1.record()
                 brackets.append(("fwd", e0, e1))
-            if dt != torch.bfloat16:
+            if dt != torch.bfloat16 and not owned:
                 gv.zero_()  # grad_value is accumulated into: the zero-fill is compulsory work of the step
             if record:
                 e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,14 +423,17 @@ def main():
             if record:
                 e3.record()
                 brackets.append(("bwd", e2, e3))
-            if grad_bucket is not None:
+            if grad_bucket is not None:  # pack this layer's (synthetic, non-zero) projection gradients, reduce them async
                 n = grad_bucket.numel() // layers
+                grad_bucket[li * n:(li + 1) * n].copy_(grad_src[li * n:(li + 1) * n])
                 handles.append(dist.all_reduce(grad_bucket[li * n:(li + 1) * n], async_op=True))
         for h in handles:
             h.wait()
 
     for _ in range(args.warmup):
         step(False)
+    barrier()
+    mgpu_check = multi_gpu_selfcheck() if world > 1 else None
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -409,6 +448,10 @@ def main():
     barrier()
     launches = int(lib.msda_launch_count(0))
     clocks = sampler.stop() if rank == 0 else None
+    if grad_bucket is not None:  # the timed region's last all-reduce summed what it should have
+        expect = grad_src / (rank + 1) * (world * (world + 1) / 2)
+        if not torch.allclose(grad_bucket, expect, rtol=1e-6, atol=0):
+            raise RuntimeError("all-reduce inside the timed region produced a wrong sum")
     elapsed_ms = t0.elapsed_time(t1)
     if world > 1:
         tmax = torch.tensor([elapsed_ms], device=device)
@@ -463,10 +506,11 @@ def main():
         h_shapes, h_lsi = shapes.cpu(), lsi.cpu()
         sess = _lib.HostSession(dims, dt, device=local_rank, images_per_chunk=args.e2e_chunk or max(1, N // 16))
 
-        def e2e_step():
+        def e2e_step():  # the six layers are submitted back to back so the copy/kernel pipeline never drains between them
             for _ in range(layers):
-                sess.forward_backward(host["value"], h_shapes, h_lsi, host["loc"], host["attn"], host["gout"], h_out,
-                                      h_gv, h_gl, h_ga)
+                sess.submit(host["value"], h_shapes, h_lsi, host["loc"], host["attn"], host["gout"], h_out,
+                            h_gv, h_gl, h_ga)
+            sess.wait()
         e2e_step()
         barrier()
         w0 = time.perf_counter()
@@ -482,9 +526,40 @@ def main():
         d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gv, h_gl, h_ga)) * layers
         e2e = {"value": queries_per_step * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-               "path": "msda_host_forward_backward (pinned host buffers, chunked H2D/compute/D2H pipeline); "
-                       "device->host read = all four result tensors", "numa": numa_note}
+               "path": "msda_host_submit x layers + msda_host_wait (pinned host buffers, chunked H2D/compute/D2H "
+                       "pipeline kept full across the layers); device->host read = all four result tensors",
+               "numa": numa_note}
         sess.close()
+        # host ceiling: the same bytes with plain copies only (no kernels), H2D and D2H on two streams, all ranks at once
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        dev_in = {k: torch.empty_like(v) for k, v in sets[0].items()}
+
+        def copy_step():
+            for _ in range(layers):
+                with torch.cuda.stream(s_in):
+                    for k in host:
+                        dev_in[k].copy_(host[k], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    h_out.copy_(out, non_blocking=True), h_gv.copy_(gv, non_blocking=True)
+                    h_gl.copy_(gl, non_blocking=True), h_ga.copy_(ga, non_blocking=True)
+            s_in.synchronize(), s_out.synchronize()
+        copy_step()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(2):
+            copy_step()
+        barrier()
+        copy_s = (time.perf_counter() - w0) / 2
+        if world > 1:
+            tmax = torch.tensor([copy_s], device=device)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            copy_s = float(tmax.item())
+        e2e["copy_only_ms_per_step"] = copy_s * 1e3
+        e2e["copy_only_gbs_per_gpu"] = (h2d + d2h) / copy_s / 1e9
+        e2e["frac_of_copy_ceiling"] = copy_s / (e2e_s / e2e_steps)
+        e2e["ceiling_note"] = "copy_only = the step's H2D + D2H bytes with cudaMemcpyAsync alone (no kernels), both " \
+                              "directions concurrently, all ranks at once: the host/PCIe ceiling of this path"
+        del dev_in
         # cheap sanity: the host path and the device path computed the same thing for the last layer set
         fwd(sets[0]); torch.cuda.synchronize()
         if not torch.equal(out.cpu(), h_out):
@@ -527,7 +602,7 @@ def main():
         alt = make_layer_inputs(torch, cfg, device, 77, other)
 
         def bwd_zero(s):
-            if dt != torch.bfloat16:
+            if dt != torch.bfloat16 and not owned:
                 gv.zero_()
             bwd(s)
         f_ms, b_ms = time_pair(alt, fwd, bwd_zero)
@@ -628,7 +703,7 @@ def main():
             "hbm_gbs_per_gpu": step_gbs, "hbm_frac_step": step_gbs / peak,
             "roofline": roof_b, "roofline_fwd": roof_f, "cpu_baseline": cpu, "e2e": e2e, "extras": extras,
             "gpu_launches": launches, "kernels": {"forward": kernel_names[0], "backward": kernel_names[1]},
-            "clocks": clocks,
+            "multi_gpu_check": mgpu_check, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

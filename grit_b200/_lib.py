@@ -79,6 +79,8 @@ def load():
         lib.msda_set_tuning.argtypes = [ctypes.c_char_p, ctypes.c_int]
         lib.msda_forward.restype = ctypes.c_int
         lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint, vp]
+        lib.msda_backward_strategy.restype = ctypes.c_int
+        lib.msda_backward_strategy.argtypes = [dimsp, ctypes.c_int, ctypes.c_uint]
         lib.msda_backward_workspace_bytes.restype = ctypes.c_size_t
         lib.msda_backward_workspace_bytes.argtypes = [dimsp, ctypes.c_int, ctypes.c_uint]
         lib.msda_backward.restype = ctypes.c_int
@@ -99,6 +101,22 @@ def load():
         lib.msda_fused_backward.restype = ctypes.c_int
         lib.msda_fused_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, dimsp,
                                             ctypes.c_int, ctypes.c_uint, vp, ctypes.c_size_t, vp]
+        lib.msda_fused_forward_vr.restype = ctypes.c_int
+        lib.msda_fused_forward_vr.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, ctypes.c_int, vp, dimsp, ctypes.c_int,
+                                              ctypes.c_uint, vp]
+        lib.msda_fused_backward_vr.restype = ctypes.c_int
+        lib.msda_fused_backward_vr.argtypes = [vp, i64p, i64p, vp, vp, vp, vp, ctypes.c_int, vp, vp, vp, vp, dimsp,
+                                               ctypes.c_int, ctypes.c_uint, vp, ctypes.c_size_t, vp]
+        lib.msda_add_dropout_ln_supported.restype = ctypes.c_int
+        lib.msda_add_dropout_ln_supported.argtypes = [ctypes.c_int64]
+        lib.msda_add_dropout_ln_workspace_bytes.restype = ctypes.c_size_t
+        lib.msda_add_dropout_ln_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+        lib.msda_add_dropout_ln_forward.restype = ctypes.c_int
+        lib.msda_add_dropout_ln_forward.argtypes = [vp, vp, vp, ctypes.c_float, vp, vp, ctypes.c_float, vp, vp, vp, vp,
+                                                    ctypes.c_int64, ctypes.c_int64, vp]
+        lib.msda_add_dropout_ln_backward.restype = ctypes.c_int
+        lib.msda_add_dropout_ln_backward.argtypes = [vp, vp, vp, vp, vp, ctypes.c_float, vp, vp, vp, vp, vp, vp,
+                                                     ctypes.c_size_t, ctypes.c_int64, ctypes.c_int64, vp]
         lib.msda_host_session_create.restype = ctypes.c_int
         lib.msda_host_session_create.argtypes = [ctypes.POINTER(ctypes.c_void_p), dimsp, ctypes.c_int, ctypes.c_int,
                                                  ctypes.c_int]
@@ -299,7 +317,7 @@ def fused_dims(value, sampling_offsets, reference_points):
 
 
 def _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                   padding_mask=None, grad_output=None):
+                   padding_mask=None, grad_output=None, valid_ratios=None):
     """Why the fused kernels cannot take these tensors (a string), or None when they can.  The fused entry points do
     raw pointer arithmetic on every argument, so shapes, dtypes, devices, contiguity and alignment are all checked
     here -- the same role _check_inputs plays for msda_forward/backward."""
@@ -315,9 +333,16 @@ def _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, a
         return "value / sampling_offsets shapes disagree"
     if tuple(attn_logits.shape) != (n, lq, m, l * p):
         return f"attn_logits must be (N,Lq,M,L*P) = {(n, lq, m, l * p)}, got {tuple(attn_logits.shape)}"
-    if reference_points.dim() != 4 or tuple(reference_points.shape[:3]) != (n, lq, l) or \
-            reference_points.shape[-1] not in (2, 4):
-        return f"reference_points must be (N,Lq,L,2|4) = {(n, lq, l)} + (2|4,), got {tuple(reference_points.shape)}"
+    if valid_ratios is None:
+        if reference_points.dim() != 4 or tuple(reference_points.shape[:3]) != (n, lq, l) or \
+                reference_points.shape[-1] not in (2, 4):
+            return f"reference_points must be (N,Lq,L,2|4) = {(n, lq, l)} + (2|4,), got {tuple(reference_points.shape)}"
+    else:  # un-expanded reference points, scaled per level by the valid ratios inside the kernels
+        if reference_points.dim() != 3 or tuple(reference_points.shape[:2]) != (n, lq) or \
+                reference_points.shape[-1] not in (2, 4):
+            return f"with valid_ratios, reference_points must be (N,Lq,2|4), got {tuple(reference_points.shape)}"
+        if tuple(valid_ratios.shape) != (n, l, 2) or valid_ratios.dtype != torch.float32:
+            return f"valid_ratios must be a float32 (N,L,2) = {(n, l, 2)} tensor"
     for name, t in (("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
                     ("reference_points", reference_points)):
         if t.dtype != torch.float32:
@@ -337,6 +362,8 @@ def _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, a
         if padding_mask.dtype != torch.bool or tuple(padding_mask.shape) != (n, s):
             return f"padding_mask must be a bool (N,S) = {(n, s)} tensor"
         named.append(("padding_mask", padding_mask))
+    if valid_ratios is not None:
+        named.append(("valid_ratios", valid_ratios))
     for name, t in named:
         if t.device != value.device:
             return f"{name} is on {t.device}, value is on {value.device}"
@@ -349,11 +376,11 @@ def _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, a
 
 
 def fused_supported(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                    padding_mask=None) -> bool:
+                    padding_mask=None, valid_ratios=None) -> bool:
     """True when the fused kernels (include/msda.h: msda_fused_*) cover this problem AND the tensors are laid out the
     way the kernels index them; the module falls back to the validated reference-shaped path otherwise."""
     if _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                      padding_mask) is not None:
+                      padding_mask, valid_ratios=valid_ratios) is not None:
         return False
     dims = fused_dims(value, sampling_offsets, reference_points)
     return bool(load().msda_fused_supported(ctypes.byref(dims), _DTYPE_CODE[value.dtype],
@@ -377,29 +404,33 @@ def mask_rows_(data, mask):
     return data
 
 
-def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points):
+def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                  valid_ratios=None):
     lib = load()
-    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points)
+    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                         valid_ratios=valid_ratios)
     if why:
         raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
     with torch.cuda.device(value.device), _nvtx_range("msda_fused_forward"):
-        rc = lib.msda_fused_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_offsets),
-                                    _ptr(attn_logits), _ptr(reference_points), int(reference_points.shape[-1]),
-                                    _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], 0,
-                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = lib.msda_fused_forward_vr(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+                                       _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
+                                       _ptr(valid_ratios) if valid_ratios is not None else None,
+                                       int(reference_points.shape[-1]), _ptr(out), ctypes.byref(dims),
+                                       _DTYPE_CODE[value.dtype], 0,
+                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc:
         _raise(lib, rc, "msda_fused_forward")
     return out
 
 
 def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                   grad_output, flags: int = 0):
+                   grad_output, flags: int = 0, valid_ratios=None):
     lib = load()
     why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                         grad_output=grad_output)
+                         grad_output=grad_output, valid_ratios=valid_ratios)
     if why:
         raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
@@ -414,8 +445,9 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
         grad_value = torch.zeros_like(value)
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device), _nvtx_range("msda_fused_backward"):
-        rc = lib.msda_fused_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
+        rc = lib.msda_fused_backward_vr(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
                                      _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
+                                     _ptr(valid_ratios) if valid_ratios is not None else None,
                                      int(reference_points.shape[-1]), _ptr(grad_output), _ptr(grad_value),
                                      _ptr(grad_offs), _ptr(grad_logits), ctypes.byref(dims), code, flags,
                                      _ptr(workspace) if workspace is not None else None, ws_bytes,
@@ -423,6 +455,62 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
     if rc:
         _raise(lib, rc, "msda_fused_backward")
     return grad_value, grad_offs, grad_logits
+
+
+def add_dropout_ln_supported(x, z, weight, bias, keep=None) -> bool:
+    """True when msda_add_dropout_ln_* (include/msda.h) can take these tensors as they are."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2):
+        return False
+    c = x.shape[-1]
+    tensors = [x, z, weight, bias] + ([keep] if keep is not None else [])
+    if z.shape != x.shape or z.dtype != x.dtype or weight is None or bias is None:
+        return False
+    if tuple(weight.shape) != (c,) or tuple(bias.shape) != (c,) or weight.dtype != x.dtype or bias.dtype != x.dtype:
+        return False
+    if keep is not None and (keep.dtype != torch.bool or keep.shape != x.shape):
+        return False
+    if any(t.device != x.device or not t.is_contiguous() or t.data_ptr() % 16 for t in tensors):
+        return False
+    return bool(load().msda_add_dropout_ln_supported(c))
+
+
+def add_dropout_ln_forward(x, z, keep, keep_scale, weight, bias, eps, save_for_backward):
+    """y = LayerNorm(x + keep*keep_scale*z); returns (y, h, mean, rstd) -- the last three None in inference."""
+    lib = load()
+    c = x.shape[-1]
+    rows = x.numel() // c
+    y = torch.empty_like(x)
+    h = torch.empty_like(x) if save_for_backward else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_for_backward else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_for_backward else None
+    opt = lambda t: _ptr(t) if t is not None else None
+    with torch.cuda.device(x.device), _nvtx_range("msda_add_dropout_ln_forward"):
+        rc = lib.msda_add_dropout_ln_forward(_ptr(x), _ptr(z), opt(keep), float(keep_scale), _ptr(weight), _ptr(bias),
+                                             float(eps), _ptr(y), opt(h), opt(mean), opt(rstd), rows, c,
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_add_dropout_ln_forward")
+    return y, h, mean, rstd
+
+
+def add_dropout_ln_backward(grad_y, h, mean, rstd, keep, keep_scale, weight):
+    """-> (grad_x, grad_z, grad_weight, grad_bias)."""
+    lib = load()
+    c = h.shape[-1]
+    rows = h.numel() // c
+    grad_x, grad_z = torch.empty_like(h), torch.empty_like(h)
+    grad_w, grad_b = torch.empty_like(weight), torch.empty_like(weight)
+    ws_bytes = lib.msda_add_dropout_ln_workspace_bytes(rows, c)
+    ws = torch.empty(max(ws_bytes // 4, 4), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device), _nvtx_range("msda_add_dropout_ln_backward"):
+        rc = lib.msda_add_dropout_ln_backward(_ptr(grad_y), _ptr(h), _ptr(mean), _ptr(rstd),
+                                              _ptr(keep) if keep is not None else None, float(keep_scale),
+                                              _ptr(weight), _ptr(grad_x), _ptr(grad_z), _ptr(grad_w), _ptr(grad_b),
+                                              _ptr(ws), ws_bytes, rows, c,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_add_dropout_ln_backward")
+    return grad_x, grad_z, grad_w, grad_b
 
 
 class HostSession:

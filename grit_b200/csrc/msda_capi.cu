@@ -12,6 +12,7 @@
 #include <cstring>
 
 #include "msda_kernels_fused.cuh"
+#include "msda_kernels_layer.cuh"
 #include "msda_kernels_staged.cuh"
 
 #include <atomic>
@@ -73,12 +74,14 @@ constexpr int kWarps = 8;
 
 // Process-wide A/B knobs (msda_set_tuning).  Defaults are the measured best on B200 (profiles/); they exist for
 // benchmarking and tests, results do not depend on them beyond fp rounding.
-std::atomic<int> g_variant{5};        // forward: 5 = lean row kernel (default) | 3 = persistent shared-memory-staged
+std::atomic<int> g_variant{0};        // forward: 0 = auto (default) | 5 = lean row kernel | 3 = persistent shared-memory-staged
 std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 1024
 std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
-std::atomic<int> g_bin_min_rows{1024};   // auto: binned coarse levels when num_query >= this
+std::atomic<int> g_staged_min_rows{600};  // auto: staged forward (fp32, D=32) when num_heads*num_query / #SMs >= this
+std::atomic<int> g_bin_min_rows{0};      // auto: binned coarse levels when num_query >= this; 0 = never (measured slower
+                                         // than the plain row kernel on B200)
 std::atomic<int> g_owned_max_taps{4};    // auto: owned when taps per value pixel (Lq*L*P*4 / S) <= this
 
 struct Geometry {
@@ -389,9 +392,16 @@ int choose_bwd_mode(const msda_dims *d, int dtype, unsigned flags)
     const bool can_own = owned_plan(d, &op);
     if (forced == BWD_BINNED) return can_bin ? BWD_BINNED : BWD_ROW;
     if (forced == BWD_OWNED) return can_own ? BWD_OWNED : BWD_ROW;
+    // owned pays where the row path's zero-fill / workspace / fold traffic dominates: sparse problems in bf16 (fp32
+    // image of grad_value zero-filled, accumulated, read back, folded) that are large enough to be bandwidth- rather
+    // than launch-bound.  For fp32 both strategies write grad_value once and measure the same.
     const int64_t taps = d->num_query * d->num_levels * d->num_point * 4;
-    if (can_own && taps <= (int64_t)g_owned_max_taps.load() * d->spatial_size) return BWD_OWNED;
-    if (can_bin && d->num_levels >= 2 && d->num_query >= g_bin_min_rows.load()) return BWD_BINNED;
+    const int64_t value_bytes = d->batch * d->spatial_size * d->num_heads * d->channels * 2;
+    if (can_own && dtype == MSDA_BF16 && value_bytes >= ((int64_t)64 << 20) &&
+        taps <= (int64_t)g_owned_max_taps.load() * d->spatial_size)
+        return BWD_OWNED;
+    const int bin_min = g_bin_min_rows.load();
+    if (can_bin && bin_min > 0 && d->num_levels >= 2 && d->num_query >= bin_min) return BWD_BINNED;
     return BWD_ROW;
 }
 
@@ -490,6 +500,7 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "hoist")) knob = &g_hoist;
     if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
     if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
+    if (key && !strcmp(key, "staged_min_rows")) knob = &g_staged_min_rows;
     if (key && !strcmp(key, "owned_max_taps")) knob = &g_owned_max_taps;
     if (!knob) return -1;
     return knob->exchange(value);
@@ -519,7 +530,12 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        if (g_variant.load() == 3) {
+        // The staged forward pays off when every persistent CTA sees enough rows per staged (image, head) plane and the
+        // taps are full 128-byte lines (fp32, D=32): measured 1.40 vs 1.47 ms at 800x1333, slower at 384x640 and in bf16.
+        const int variant = g_variant.load();
+        const bool staged_auto = variant == 0 && dtype == MSDA_F32 && dims->channels == 32 &&
+                                 dims->num_heads * dims->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms;
+        if (variant == 3 || staged_auto) {
             const int rc = dtype == MSDA_F32
                                ? launch_fwd_staged<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
                                                           attn_weight, output, st)
@@ -547,6 +563,12 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     }
     ++tl_launches;
     return check_cuda(cudaPeekAtLastError(), "msda_forward launch");
+}
+
+int msda_backward_strategy(const msda_dims *dims, int dtype, unsigned flags)
+{
+    if (check_dims(dims, dtype) != MSDA_OK) return 0;
+    return choose_bwd_mode(dims, dtype, flags);
 }
 
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags)
@@ -880,20 +902,22 @@ namespace {
 
 template <typename T, int DD, int LL, int PP, int RD>
 void fused_fwd_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi,
-                      const void *offs, const void *logits, const void *ref, void *out, cudaStream_t st)
+                      const void *offs, const void *logits, const void *ref, const void *vratio, void *out,
+                      cudaStream_t st)
 {
     constexpr int W = 4;
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
     msda::msda_fwd_fused<T, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
-        (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref, (T *)out,
-        (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
+        (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
+        (const float *)vratio, (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
     snprintf(tl_kernel, sizeof(tl_kernel), "fwd_fused<%s,D%d,L%d,P%d,ref%d>", tname<T>(), DD, LL, PP, RD);
 }
 
 template <typename T, int DD, int LL, int PP, int RD>
 void fused_bwd_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi,
-                      const void *offs, const void *logits, const void *ref, const void *gout, void *gv_acc,
+                      const void *offs, const void *logits, const void *ref, const void *vratio, const void *gout,
+                      void *gv_acc,
                       const float *det_scale, void *goffs, void *glogits, cudaStream_t st)
 {
     constexpr int W = 4;
@@ -903,12 +927,12 @@ void fused_bwd_launch(const msda_dims *d, const void *value, const int64_t *shap
     if (det_scale)
         msda::msda_bwd_fused<T, CH, msda::AccFix64, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
-            (const T *)gout, (unsigned long long *)gv_acc, det_scale, (float *)goffs, (float *)glogits,
+            (const float *)vratio, (const T *)gout, (unsigned long long *)gv_acc, det_scale, (float *)goffs, (float *)glogits,
             (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
     else
         msda::msda_bwd_fused<T, CH, msda::AccF32, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
-            (const T *)gout, (float *)gv_acc, nullptr, (float *)goffs, (float *)glogits, (int)d->spatial_size,
+            (const float *)vratio, (const T *)gout, (float *)gv_acc, nullptr, (float *)goffs, (float *)glogits, (int)d->spatial_size,
             (int)d->num_heads, (int)d->num_query, rpi);
     snprintf(tl_kernel, sizeof(tl_kernel), "bwd_fused<%s,D%d,L%d,P%d,ref%d%s>", tname<T>(), DD, LL, PP, RD,
              det_scale ? ",deterministic" : "");
@@ -918,9 +942,10 @@ void fused_bwd_launch(const msda_dims *d, const void *value, const int64_t *shap
 
 extern "C" {
 
-int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                       const void *sampling_offsets, const void *attn_logits, const void *reference_points,
-                       int ref_dim, void *output, const msda_dims *dims, int dtype, unsigned flags, void *cuda_stream)
+int msda_fused_forward_vr(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                          const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                          const void *valid_ratios, int ref_dim, void *output, const msda_dims *dims, int dtype,
+                          unsigned flags, void *cuda_stream)
 {
     tl_error[0] = 0;
     (void)flags;
@@ -936,39 +961,39 @@ int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const i
         !output)
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
     if (!aligned16(value) || !aligned16(output) || !aligned16(reference_points) ||
-        (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u))
+        (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u) || (reinterpret_cast<uintptr_t>(valid_ratios) & 7u))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned value/output/reference_points");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-#define X(DD, LL, PP)                                                                                             \
-    if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) {                         \
-        if (dtype == MSDA_F32)                                                                                    \
-            ref_dim == 2 ? fused_fwd_launch<float, DD, LL, PP, 2>(dims, value, spatial_shapes, level_start_index, \
-                                                                  sampling_offsets, attn_logits, reference_points, \
-                                                                  output, st)                                     \
-                         : fused_fwd_launch<float, DD, LL, PP, 4>(dims, value, spatial_shapes, level_start_index, \
-                                                                  sampling_offsets, attn_logits, reference_points, \
-                                                                  output, st);                                    \
-        else                                                                                                      \
-            ref_dim == 2 ? fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 2>(dims, value, spatial_shapes,            \
-                                                                          level_start_index, sampling_offsets,    \
-                                                                          attn_logits, reference_points, output,  \
-                                                                          st)                                     \
-                         : fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 4>(dims, value, spatial_shapes,            \
-                                                                          level_start_index, sampling_offsets,    \
-                                                                          attn_logits, reference_points, output,  \
-                                                                          st);                                    \
+#define ARGS dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, valid_ratios, output, st
+#define X(DD, LL, PP)                                                                                 \
+    if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) {             \
+        if (dtype == MSDA_F32)                                                                        \
+            ref_dim == 2 ? fused_fwd_launch<float, DD, LL, PP, 2>(ARGS)                               \
+                         : fused_fwd_launch<float, DD, LL, PP, 4>(ARGS);                              \
+        else                                                                                          \
+            ref_dim == 2 ? fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 2>(ARGS)                       \
+                         : fused_fwd_launch<__nv_bfloat16, DD, LL, PP, 4>(ARGS);                      \
     }
     MSDA_FOR_EACH_FUSED_SPEC(X)
 #undef X
+#undef ARGS
     ++tl_launches;
     return check_cuda(cudaPeekAtLastError(), "msda_fused_forward launch");
 }
 
-int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                        const void *sampling_offsets, const void *attn_logits, const void *reference_points,
-                        int ref_dim, const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits,
-                        const msda_dims *dims, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
-                        void *cuda_stream)
+int msda_fused_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                       int ref_dim, void *output, const msda_dims *dims, int dtype, unsigned flags, void *cuda_stream)
+{
+    return msda_fused_forward_vr(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                 reference_points, nullptr, ref_dim, output, dims, dtype, flags, cuda_stream);
+}
+
+int msda_fused_backward_vr(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                           const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                           const void *valid_ratios, int ref_dim, const void *grad_output, void *grad_value,
+                           void *grad_offsets, void *grad_logits, const msda_dims *dims, int dtype, unsigned flags,
+                           void *workspace, size_t workspace_bytes, void *cuda_stream)
 {
     tl_error[0] = 0;
     if (int rc = check_dims(dims, dtype)) return rc;
@@ -984,15 +1009,15 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
         return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
     if (!aligned16(value) || !aligned16(grad_output) || !aligned16(grad_value) || !aligned16(workspace) ||
         !aligned16(reference_points) || (reinterpret_cast<uintptr_t>(sampling_offsets) & 7u) ||
-        (reinterpret_cast<uintptr_t>(grad_offsets) & 7u))
+        (reinterpret_cast<uintptr_t>(grad_offsets) & 7u) || (reinterpret_cast<uintptr_t>(valid_ratios) & 7u))
         return fail(MSDA_ERR_INVALID_ARGUMENT, "fused kernels need 16-byte aligned tensors");
     AccPlan plan;
     if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, nullptr, grad_output, st,
                            &plan))
         return rc;
 #define ARGS                                                                                                    \
-    dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, grad_output, \
-        plan.gv_acc, plan.det_scale, grad_offsets, grad_logits, st
+    dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, valid_ratios, \
+        grad_output, plan.gv_acc, plan.det_scale, grad_offsets, grad_logits, st
 #define X(DD, LL, PP)                                                                                 \
     if (dims->channels == (DD) && dims->num_levels == (LL) && dims->num_point == (PP)) {             \
         if (dtype == MSDA_F32)                                                                        \
@@ -1008,6 +1033,112 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
     ++tl_launches;
     if (int rc = check_cuda(cudaPeekAtLastError(), "msda_fused_backward launch")) return rc;
     return acc_end(dims, dtype, flags, grad_value, workspace, plan, st);
+}
+
+int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                        const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                        int ref_dim, const void *grad_output, void *grad_value, void *grad_offsets, void *grad_logits,
+                        const msda_dims *dims, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
+                        void *cuda_stream)
+{
+    return msda_fused_backward_vr(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                  reference_points, nullptr, ref_dim, grad_output, grad_value, grad_offsets,
+                                  grad_logits, dims, dtype, flags, workspace, workspace_bytes, cuda_stream);
+}
+
+// ---- decoder-layer epilogue: y = LayerNorm(x + dropout(z)) (msda_kernels_layer.cuh) -----------------------------------
+
+static int ln_blocks(int64_t rows)
+{
+    int64_t b = (rows + 7) / 8;
+    return (int)(b < 1 ? 1 : (b > 1024 ? 1024 : b));
+}
+
+size_t msda_add_dropout_ln_workspace_bytes(int64_t rows, int64_t channels)
+{
+    if (rows <= 0 || channels <= 0) return 0;
+    return (size_t)ln_blocks(rows) * 2 * (size_t)channels * sizeof(float);
+}
+
+int msda_add_dropout_ln_supported(int64_t channels) { return channels > 0 && channels % 128 == 0 && channels <= 512; }
+
+int msda_add_dropout_ln_forward(const void *x, const void *z, const unsigned char *keep, float keep_scale,
+                                const void *gamma, const void *beta, float eps, void *y, void *h_saved, void *mean,
+                                void *rstd, int64_t rows, int64_t channels, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "negative row count");
+    if (!msda_add_dropout_ln_supported(channels))
+        return fail(MSDA_ERR_UNSUPPORTED, "add+dropout+LayerNorm supports channels in {128, 256, 384, 512}, got %lld",
+                    (long long)channels);
+    if (rows == 0) return MSDA_OK;
+    if (!x || !z || !gamma || !beta || !y) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    if ((h_saved != nullptr) != (mean != nullptr) || (mean != nullptr) != (rstd != nullptr))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "h_saved, mean and rstd must be given together (training) or all be null");
+    if (!aligned16(x) || !aligned16(z) || !aligned16(y) || !aligned16(gamma) || !aligned16(beta) || !aligned16(h_saved) ||
+        (reinterpret_cast<uintptr_t>(keep) & 3u))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "add+dropout+LayerNorm needs 16-byte aligned tensors");
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+#define LAUNCH(V)                                                                                                     \
+    msda::msda_add_dropout_ln_fwd<V><<<grid, 256, 0, st>>>((const float *)x, (const float *)z, keep, keep_scale,      \
+                                                           (const float *)gamma, (const float *)beta, eps, (float *)y, \
+                                                           (float *)h_saved, (float *)mean, (float *)rstd, rows)
+    switch (channels / 128) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        default: LAUNCH(4); break;
+    }
+#undef LAUNCH
+    ++tl_launches;
+    snprintf(tl_kernel, sizeof(tl_kernel), "add_dropout_ln_fwd<C%d>", (int)channels);
+    return check_cuda(cudaPeekAtLastError(), "msda_add_dropout_ln_forward launch");
+}
+
+int msda_add_dropout_ln_backward(const void *grad_y, const void *h_saved, const void *mean, const void *rstd,
+                                 const unsigned char *keep, float keep_scale, const void *gamma, void *grad_x,
+                                 void *grad_z, void *grad_gamma, void *grad_beta, void *workspace,
+                                 size_t workspace_bytes, int64_t rows, int64_t channels, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (rows < 0) return fail(MSDA_ERR_INVALID_ARGUMENT, "negative row count");
+    if (!msda_add_dropout_ln_supported(channels))
+        return fail(MSDA_ERR_UNSUPPORTED, "add+dropout+LayerNorm supports channels in {128, 256, 384, 512}, got %lld",
+                    (long long)channels);
+    if (!grad_gamma || !grad_beta) return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (rows == 0) {
+        cudaMemsetAsync(grad_gamma, 0, (size_t)channels * 4, st);
+        return check_cuda(cudaMemsetAsync(grad_beta, 0, (size_t)channels * 4, st), "memset");
+    }
+    if (!grad_y || !h_saved || !mean || !rstd || !gamma || !grad_x || !grad_z)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
+    const size_t need = msda_add_dropout_ln_workspace_bytes(rows, channels);
+    if (!workspace || workspace_bytes < need)
+        return fail(MSDA_ERR_WORKSPACE, "add+dropout+LayerNorm backward needs a %zu-byte workspace, got %zu", need,
+                    workspace_bytes);
+    if (!aligned16(grad_y) || !aligned16(h_saved) || !aligned16(grad_x) || !aligned16(grad_z) || !aligned16(gamma) ||
+        !aligned16(workspace) || (reinterpret_cast<uintptr_t>(keep) & 3u))
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "add+dropout+LayerNorm needs 16-byte aligned tensors");
+    const int blocks = ln_blocks(rows);
+#define LAUNCH(V)                                                                                                    \
+    msda::msda_add_dropout_ln_bwd<V><<<blocks, 256, 0, st>>>((const float *)grad_y, (const float *)h_saved,          \
+                                                             (const float *)mean, (const float *)rstd, keep,          \
+                                                             keep_scale, (const float *)gamma, (float *)grad_x,       \
+                                                             (float *)grad_z, (float *)workspace, rows)
+    switch (channels / 128) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        default: LAUNCH(4); break;
+    }
+#undef LAUNCH
+    msda::msda_ln_param_grads<<<(unsigned)((channels + 127) / 128), 128, 0, st>>>(
+        (const float *)workspace, blocks, (int)channels, (float *)grad_gamma, (float *)grad_beta);
+    tl_launches += 2;
+    snprintf(tl_kernel, sizeof(tl_kernel), "add_dropout_ln_bwd<C%d>", (int)channels);
+    return check_cuda(cudaPeekAtLastError(), "msda_add_dropout_ln_backward launch");
 }
 
 // ---- host-buffer session ---------------------------------------------------------------------------

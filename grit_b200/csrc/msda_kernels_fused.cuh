@@ -8,6 +8,9 @@
 // and the resolver lane of each sample point does softmax (two shuffle reductions over the row's L*P lanes) and
 //     loc = ref.xy + off / (W_l, H_l)                    2-d reference points   (reference :105-108)
 //     loc = ref.xy + off / P * ref.wh * 0.5              4-d reference boxes    (reference :109-111)
+// (with `vratio` != nullptr the reference points arrive un-expanded, (N, Lq, 2|4), and are scaled by the level's valid
+// ratio here -- DeformableTransformerDecoderLayer.forward, models/detection/det_module.py:323-328 -- instead of being
+// materialised as (N, Lq, L, 2|4) by the caller)
 // in registers; sampling_locations / attention_weights are never materialised.  The backward emits grad_offsets and
 // grad_logits directly (softmax backward = one extra warp reduction per row); grad of the reference points, when
 // needed, is a cheap reduction of grad_offsets done by the caller.  The padding mask is applied by msda_mask_rows
@@ -33,10 +36,37 @@ __device__ __forceinline__ float segment_sum(float v)
     return v;
 }
 
+// Reference point (box) of query bq at level rl: either stored per level, or stored once and scaled by the valid ratio.
+template <int L, int RD>
+__device__ __forceinline__ float4 load_ref(const float *__restrict__ ref, const float *__restrict__ vratio, int64_t bq,
+                                           int n, int rl)
+{
+    float4 rf = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vratio == nullptr) {
+        if (RD == 2) {
+            const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + bq * L + rl);
+            rf.x = r.x, rf.y = r.y;
+        } else {
+            rf = __ldg(reinterpret_cast<const float4 *>(ref) + bq * L + rl);
+        }
+    } else {
+        const float2 vr = __ldg(reinterpret_cast<const float2 *>(vratio) + (int64_t)n * L + rl);
+        if (RD == 2) {
+            const float2 r = __ldg(reinterpret_cast<const float2 *>(ref) + bq);
+            rf.x = r.x * vr.x, rf.y = r.y * vr.y;
+        } else {
+            const float4 r = __ldg(reinterpret_cast<const float4 *>(ref) + bq);
+            rf = make_float4(r.x * vr.x, r.y * vr.y, r.z * vr.x, r.w * vr.y);
+        }
+    }
+    return rf;
+}
+
 // Softmax weight and sampling location of point `rp` of row `row`, from the Linears' raw outputs.
 template <int L, int P, int RD>
 __device__ __forceinline__ void fused_point(const float *__restrict__ offs, const float *__restrict__ logits,
-                                            const float *__restrict__ ref, int64_t row, int64_t bq, int rp, int rl,
+                                            const float *__restrict__ ref, const float *__restrict__ vratio, int n,
+                                            int64_t row, int64_t bq, int rp, int rl,
                                             int H, int W, float &a_soft, float &x, float &y)
 {
     constexpr int LP = L * P;
@@ -45,12 +75,11 @@ __device__ __forceinline__ void fused_point(const float *__restrict__ offs, cons
     const float ex = exp2f((lg - mx) * 1.4426950408889634f);
     a_soft = ex / segment_sum<LP>(ex);
     const float2 of = __ldg(reinterpret_cast<const float2 *>(offs) + row * LP + rp);
+    const float4 rf = load_ref<L, RD>(ref, vratio, bq, n, rl);
     if (RD == 2) {
-        const float2 rf = __ldg(reinterpret_cast<const float2 *>(ref) + bq * L + rl);
         x = rf.x + of.x / (float)W;
         y = rf.y + of.y / (float)H;
     } else {
-        const float4 rf = __ldg(reinterpret_cast<const float4 *>(ref) + bq * L + rl);
         x = rf.x + of.x / (float)P * rf.z * 0.5f;
         y = rf.y + of.y / (float)P * rf.w * 0.5f;
     }
@@ -60,7 +89,7 @@ template <typename T, int D, int L, int P, int WARPS, int RD>
 __global__ void __launch_bounds__(WARPS * 32)
 msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
-               T *__restrict__ out, int S, int M, int Lq, unsigned rows_per_image)
+               const float *__restrict__ vratio, T *__restrict__ out, int S, int M, int Lq, unsigned rows_per_image)
 {
     constexpr int E = Chunk<T>::E;
     constexpr int LPT = D / E;
@@ -86,7 +115,7 @@ msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const int rp = lane % LP;
     const int rl = rp / P;
     float a_soft, x, y;
-    fused_point<L, P, RD>(offs, logits, ref, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
     const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
 
     float acc[E];
@@ -108,7 +137,7 @@ template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS,
 __global__ void __launch_bounds__(WARPS * 32, 1024 / (WARPS * 32))
 msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
-               const T *__restrict__ grad_out, typename ACC::elem *__restrict__ gv_acc,
+               const float *__restrict__ vratio, const T *__restrict__ grad_out, typename ACC::elem *__restrict__ gv_acc,
                const float *__restrict__ det_scale, float *__restrict__ grad_offs, float *__restrict__ grad_logits,
                int S, int M, int Lq, unsigned rows_per_image)
 {
@@ -143,7 +172,7 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const int rp = lane % LP;
     const int rl = rp / P;
     float a_soft, x, y;
-    fused_point<L, P, RD>(offs, logits, ref, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
     const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
 
     float go[E];
@@ -170,7 +199,7 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
         grad_logits[row * LP + pt] = a_pt * (part[0] - dot);
         float gx = part[1], gy = part[2];  // 2-d: d loc/d off = 1/(W,H) cancels the (W,H) of d(w_im,h_im)/d loc
         if (RD == 4) {
-            const float4 rf = __ldg(reinterpret_cast<const float4 *>(ref) + bq * L + l);
+            const float4 rf = load_ref<L, RD>(ref, vratio, bq, (int)blockIdx.y, l);
             gx = (float)sW[l] * gx * (rf.z * 0.5f / (float)P);
             gy = (float)sH[l] * gy * (rf.w * 0.5f / (float)P);
         }

@@ -1,2 +1,3 @@
-from .ms_deform_attn_func import (MSDeformAttnFunction, MSDeformAttnFusedFunction, PackLevelsFunction,  # noqa: F401
+from .ms_deform_attn_func import (AddDropoutLayerNormFunction, MSDeformAttnFunction,  # noqa: F401
+                                  MSDeformAttnFusedFunction, PackLevelsFunction, add_dropout_layer_norm,
                                   ms_deform_attn_core_pytorch, pack_levels, set_deterministic)

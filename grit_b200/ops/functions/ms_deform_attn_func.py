@@ -96,21 +96,26 @@ class MSDeformAttnFusedFunction(Function):
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_offsets, attn_logits,
-                reference_points, padding_mask):
+                reference_points, padding_mask, valid_ratios=None):
         if padding_mask is not None:
             # in-place write: `value` is the value_proj output, whose producer (addmm) does not need its own output
             # in backward; the matching rows of grad_value are zeroed below
             _lib.mask_rows_(value, padding_mask)
             torch.autograd.graph.increment_version(value)
         ctx.has_mask = padding_mask is not None
+        ctx.has_vr = valid_ratios is not None
         sampling_offsets = sampling_offsets.contiguous()
         attn_logits = attn_logits.contiguous()
         reference_points = reference_points.contiguous()
+        if valid_ratios is not None:
+            valid_ratios = valid_ratios.contiguous()
         output = _lib.fused_forward(value, value_spatial_shapes, value_level_start_index, sampling_offsets,
-                                    attn_logits, reference_points)
+                                    attn_logits, reference_points, valid_ratios)
         saved = [value, value_spatial_shapes, value_level_start_index, sampling_offsets, attn_logits, reference_points]
         if padding_mask is not None:
             saved.append(padding_mask)
+        if valid_ratios is not None:
+            saved.append(valid_ratios)
         ctx.save_for_backward(*saved)
         return output
 
@@ -118,26 +123,88 @@ class MSDeformAttnFusedFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         value, shapes, lsi, offsets, logits, ref = ctx.saved_tensors[:6]
+        vr = ctx.saved_tensors[-1] if ctx.has_vr else None
         grad_value, grad_offs, grad_logits = _lib.fused_backward(value, shapes, lsi, offsets, logits, ref,
-                                                                 grad_output.contiguous(), _backward_flags(value.dtype))
+                                                                 grad_output.contiguous(), _backward_flags(value.dtype),
+                                                                 valid_ratios=vr)
         if ctx.has_mask:
             _lib.mask_rows_(grad_value, ctx.saved_tensors[6])
         grad_ref = None
         if ctx.needs_input_grad[5]:
             n_points = offsets.shape[4]
+            # per-level reference points as the kernels used them: (N, Lq, L, 2|4)
+            if vr is None:
+                ref_l = ref
+            elif ref.shape[-1] == 2:
+                ref_l = ref[:, :, None] * vr[:, None]
+            else:
+                ref_l = ref[:, :, None] * torch.cat([vr, vr], -1)[:, None]
             if ref.shape[-1] == 2:  # loc = ref + off / (W, H)  =>  d loc/d ref = 1, grad_loc = grad_off * (W, H)
                 normalizer = torch.stack([shapes[:, 1], shapes[:, 0]], -1).to(grad_offs.dtype)
-                grad_ref = (grad_offs * normalizer[None, None, None, :, None, :]).sum(dim=(2, 4))
+                grad_ref_l = (grad_offs * normalizer[None, None, None, :, None, :]).sum(dim=(2, 4))
             else:  # loc = ref.xy + off / P * ref.wh * 0.5
-                scale = ref[:, :, None, :, None, 2:] * (0.5 / n_points)
+                scale = ref_l[:, :, None, :, None, 2:] * (0.5 / n_points)
                 # (a zero-size reference box collapses every sample onto its centre and carries no offset gradient to
                 #  recover grad_loc from; its reference-point gradient is reported as 0 instead of NaN)
                 grad_loc = torch.where(scale != 0, grad_offs / torch.where(scale != 0, scale, torch.ones_like(scale)),
                                        torch.zeros_like(grad_offs))
                 grad_xy = grad_loc.sum(dim=(2, 4))
                 grad_wh = (grad_loc * offsets * (0.5 / n_points)).sum(dim=(2, 4))
-                grad_ref = torch.cat([grad_xy, grad_wh], -1)
-        return grad_value, None, None, grad_offs, grad_logits, grad_ref, None
+                grad_ref_l = torch.cat([grad_xy, grad_wh], -1)
+            if vr is None:
+                grad_ref = grad_ref_l
+            elif ref.shape[-1] == 2:  # ref_l = ref * vr[l]  =>  grad_ref = sum_l grad_ref_l * vr[l]
+                grad_ref = (grad_ref_l * vr[:, None]).sum(2)
+            else:
+                grad_ref = (grad_ref_l * torch.cat([vr, vr], -1)[:, None]).sum(2)
+        return grad_value, None, None, grad_offs, grad_logits, grad_ref, None, None
+
+
+class AddDropoutLayerNormFunction(Function):
+    """``LayerNorm(x + dropout(z))`` in one kernel each way (include/msda.h: msda_add_dropout_ln_*) --
+    the epilogue that follows every attention / FFN block of the reference's DeformableTransformerDecoderLayer
+    (models/detection/det_module.py:316-318, 331-333, 337-339).  ``keep`` is the dropout mask (bool, same shape) or
+    None; ``keep_scale`` = 1/(1-p)."""
+
+    @staticmethod
+    def forward(ctx, x, z, keep, keep_scale, weight, bias, eps):
+        need_grad = any(ctx.needs_input_grad[i] for i in (0, 1, 4, 5))
+        y, h, mean, rstd = _lib.add_dropout_ln_forward(x, z, keep, keep_scale, weight, bias, eps, need_grad)
+        ctx.keep_scale = keep_scale
+        ctx.has_keep = keep is not None
+        if need_grad:
+            ctx.save_for_backward(*([h, mean, rstd, weight] + ([keep] if keep is not None else [])))
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_y):
+        h, mean, rstd, weight = ctx.saved_tensors[:4]
+        keep = ctx.saved_tensors[4] if ctx.has_keep else None
+        grad_x, grad_z, grad_w, grad_b = _lib.add_dropout_ln_backward(grad_y.contiguous(), h, mean, rstd, keep,
+                                                                      ctx.keep_scale, weight)
+        return grad_x, grad_z, None, None, grad_w, grad_b, None
+
+
+def add_dropout_layer_norm(x, z, norm, p=0.0, training=False):
+    """``norm(x + F.dropout(z, p, training))`` for an ``nn.LayerNorm`` ``norm`` -- one fused kernel when the tensors
+    qualify (CUDA fp32, contiguous, 16-byte aligned, channels in {128, 256, 384, 512}, affine LayerNorm over the last
+    dimension), the plain PyTorch composition otherwise.  In training the dropout mask is drawn from torch's own
+    generator exactly as ``nn.Dropout`` would draw it for a tensor of this shape (``F.dropout`` on ones), so a seeded
+    run reproduces the reference's mask."""
+    import torch.nn.functional as F
+    use_dropout = training and p > 0.0
+    if norm.weight is not None and norm.bias is not None and tuple(norm.normalized_shape) == (x.shape[-1],):
+        xc, zc = x.contiguous(), z.contiguous()
+        keep = None
+        if use_dropout:
+            keep = F.dropout(torch.ones_like(zc), p, True) != 0
+        if _lib.add_dropout_ln_supported(xc, zc, norm.weight, norm.bias, keep):
+            scale = 1.0 / (1.0 - p) if use_dropout else 1.0
+            return AddDropoutLayerNormFunction.apply(xc, zc, keep, scale, norm.weight, norm.bias, norm.eps)
+        if use_dropout:  # same mask, unfused
+            return norm(x + z * keep.to(z.dtype) * (1.0 / (1.0 - p)))
+    return norm(x + F.dropout(z, p, training))
 
 
 class PackLevelsFunction(Function):

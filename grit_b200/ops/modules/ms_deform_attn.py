@@ -77,7 +77,7 @@ class MSDeformAttn(nn.Module):
         constant_(self.output_proj.bias.data, 0.)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None, value=None):
+                input_padding_mask=None, value=None, valid_ratios=None):
         """
         :param query                    (N, Length_{query}, C)
         :param reference_points         (N, Length_{query}, n_levels, 2) in [0, 1], top-left (0,0), bottom-right (1,1),
@@ -91,6 +91,12 @@ class MSDeformAttn(nn.Module):
                                         memory, det_module.py:191-198, so one batched GEMM can serve all of them).  Not in
                                         the reference signature; ``None`` gives the reference behaviour.  A supplied
                                         tensor is never modified (the padding mask is applied to a copy).
+        :param valid_ratios             optional (N, n_levels, 2) [w-ratio, h-ratio]: ``reference_points`` is then the
+                                        UN-EXPANDED (N, Length_{query}, 2|4) tensor and level l uses
+                                        ``reference_points * valid_ratios[:, l]`` -- the scaling the reference's decoder
+                                        layer does before calling this module (det_module.py:323-328), done inside the
+                                        fused kernels instead of materialising (N, Lq, n_levels, 2|4).  Not in the
+                                        reference signature.
         :return output                  (N, Length_{query}, C)
         """
         N, Len_q, _ = query.shape
@@ -116,12 +122,17 @@ class MSDeformAttn(nn.Module):
             if mask is not None and not own_value:
                 value, mask = value.masked_fill(mask[..., None], float(0)), None
             value4 = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-            ref32 = reference_points.float().expand(N, Len_q, self.n_levels, reference_points.shape[-1]).contiguous()
+            if valid_ratios is None:
+                ref32 = reference_points.float().expand(N, Len_q, self.n_levels,
+                                                        reference_points.shape[-1]).contiguous()
+                vr32 = None
+            else:
+                ref32, vr32 = reference_points.float().contiguous(), valid_ratios.float().contiguous()
             offs32, logits32 = sampling_offsets.float().contiguous(), attention_weights.float().contiguous()
             if _lib.fused_supported(value4, input_spatial_shapes, input_level_start_index, offs32, logits32, ref32,
-                                    mask):
+                                    mask, vr32):
                 output = MSDeformAttnFusedFunction.apply(value4, input_spatial_shapes, input_level_start_index,
-                                                         offs32, logits32, ref32, mask)
+                                                         offs32, logits32, ref32, mask, vr32)
                 return self.output_proj(output)
             if mask is None:
                 input_padding_mask = None  # already applied above
@@ -129,6 +140,9 @@ class MSDeformAttn(nn.Module):
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.contiguous().view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
+        if valid_ratios is not None:  # the reference decoder layer's expansion (det_module.py:323-328)
+            vr = valid_ratios if reference_points.shape[-1] == 2 else torch.cat([valid_ratios, valid_ratios], -1)
+            reference_points = reference_points[:, :, None] * vr[:, None]
 
         if reference_points.shape[-1] == 2:
             offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)
@@ -142,20 +156,26 @@ class MSDeformAttn(nn.Module):
         return self.output_proj(output)
 
 
-def hoisted_value_proj(modules, input_flatten):
+def hoisted_value_proj(modules, input_flatten, padding_mask=None):
     """``value_proj`` of several MSDeformAttn layers that read the SAME memory, as ONE GEMM.
 
     GRIT's decoder runs six layers over an unchanged ``src`` (models/detection/det_module.py:191-198); each layer's
     ``value_proj`` is an (N*S, C) x (C, C) GEMM that re-reads ``src``.  Concatenating the weight matrices gives one
-    (N*S, C) x (C, n*C) GEMM that reads ``src`` once.  Returns a tuple of per-layer ``value`` tensors (N, S, C), each
-    contiguous (the kernels need (N, S, M, D) contiguous, so the GEMM output is re-laid out layer-major once).
+    batched GEMM (n launches -> 1).  Returns a tuple of per-layer ``value`` tensors (N, S, C), each contiguous.
     Pass ``value=vals[i]`` to layer i.  Gradients reach every layer's ``value_proj.weight/bias`` and ``input_flatten``
-    through autograd.
+    through autograd.  With ``padding_mask`` (N, S) the masked pixels are zeroed here, once for all layers (the
+    reference's ``value.masked_fill``, modules/ms_deform_attn.py:96-97); pass ``input_padding_mask=None`` to the layers then.
     """
     modules = list(modules)
-    weight = torch.cat([m.value_proj.weight for m in modules], 0)  # (n*C, C)
-    bias = torch.cat([m.value_proj.bias for m in modules], 0)
     n_layers, c = len(modules), modules[0].d_model
-    out = F.linear(input_flatten, weight, bias)  # (N, S, n*C)
     n, s_len, _ = input_flatten.shape
-    return out.view(n, s_len, n_layers, c).permute(2, 0, 1, 3).contiguous().unbind(0)
+    # One batched GEMM whose output is already layer-major and contiguous per layer -- (n_layers, N*S, C) -- which is the
+    # (N, S, M, D) layout the kernels index; a single (N*S, C) x (C, n*C) GEMM would need a strided re-layout copy of
+    # all n outputs afterwards (measured: slower than n separate GEMMs at batch 64).
+    weight_t = torch.stack([m.value_proj.weight.t() for m in modules], 0)  # (n, C_in, C_out)
+    bias = torch.stack([m.value_proj.bias for m in modules], 0).unsqueeze(1)  # (n, 1, C_out)
+    src = input_flatten.reshape(1, n * s_len, c).expand(n_layers, -1, -1)
+    out = torch.baddbmm(bias, src, weight_t).view(n_layers, n, s_len, c)
+    if padding_mask is not None:
+        out = out.masked_fill(padding_mask[None, ..., None], float(0))
+    return out.unbind(0)

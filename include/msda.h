@@ -92,15 +92,19 @@ const char *msda_last_kernel(void);
 int64_t msda_launch_count(int reset);
 
 /* Tuning / A-B testing knob (process-wide; for benchmarks and tests).  Keys:
- *   "variant"        forward: 5 lean row kernel (default) | 3 persistent shared-memory-staged forward
+ *   "variant"        forward: 0 auto (default: the staged forward for fp32 D=32 problems with >= "staged_min_rows"
+ *                    (image, head, query) rows per SM, else the row kernel) | 5 lean row kernel | 3 persistent
+ *                    shared-memory-staged forward
  *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
  *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
  *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
  *                    2 row kernel + on-SM aggregation of the coarse levels (msda_bwd_binned) |
  *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems)
- *   "bin_min_rows"   auto rule: mode 2 when num_query >= this      (default 1024)
- *   "owned_max_taps" auto rule: mode 3 when num_query*L*P*4 <= this * spatial_size   (default 4)
+ *   "staged_min_rows" see "variant"   (default 600)
+ *   "bin_min_rows"   auto rule: mode 2 when num_query >= this; 0 = never (default: measured slower than mode 1 on B200)
+ *   "owned_max_taps" auto rule: mode 3 for bf16 problems with num_query*L*P*4 <= this * spatial_size (default 4) and a
+ *                    grad_value of at least 64 MB (for fp32 both strategies write grad_value once and measure the same)
  * Returns the previous value, or -1 for an unknown key.  Results do not depend on the knobs beyond fp rounding. */
 int msda_set_tuning(const char *key, int value);
 
@@ -113,6 +117,14 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
  * grad_value; 0 with MSDA_FLAG_ALIGNED16 when the owned backward applies); N*S*M*D*8 + 16 with
  * MSDA_FLAG_DETERMINISTIC.  The workspace must be 16-byte aligned. */
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags);
+
+/* The strategy msda_backward will use for this problem when every tensor is 16-byte aligned (0 = invalid dims):
+ *   1  row kernel: every tap is a global vector red into a zero-filled grad_value (or workspace);
+ *   2  row kernel for the fine levels + msda_bwd_binned: coarse levels aggregated in shared memory, flushed once;
+ *   3  row kernel for grad_sampling_loc / grad_attn_weight + msda_bwd_owned: every grad_value line is written exactly
+ *      once by its owner -- no zero-fill (MSDA_FLAG_ZERO_GRAD_VALUE costs nothing), no workspace, no fold.
+ * A pure function of (dims, dtype, flags) and the msda_set_tuning knobs. */
+int msda_backward_strategy(const msda_dims *dims, int dtype, unsigned flags);
 
 /* grad_value += scatter(w*attn*grad_out); grad_sampling_loc, grad_attn_weight = analytic gradients. */
 int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
@@ -145,6 +157,41 @@ int msda_fused_backward(const void *value, const int64_t *spatial_shapes, const 
                         int ref_dim, const void *grad_output, void *grad_value, void *grad_offsets,
                         void *grad_logits, const msda_dims *dims, int dtype, unsigned flags, void *workspace,
                         size_t workspace_bytes, void *cuda_stream);
+
+/* Same, with the valid-ratio scaling of the decoder layer (models/detection/det_module.py:323-328) inside the kernels:
+ * with valid_ratios (N, L, 2) fp32 [w-ratio, h-ratio] != NULL, reference_points is the UN-EXPANDED (N, Lq, ref_dim)
+ * tensor and level l uses reference_points * valid_ratios[:, l] (both halves of a 4-d box are scaled);
+ * valid_ratios == NULL is msda_fused_forward / msda_fused_backward. */
+int msda_fused_forward_vr(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                          const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                          const void *valid_ratios, int ref_dim, void *output, const msda_dims *dims, int dtype,
+                          unsigned flags, void *cuda_stream);
+int msda_fused_backward_vr(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                           const void *sampling_offsets, const void *attn_logits, const void *reference_points,
+                           const void *valid_ratios, int ref_dim, const void *grad_output, void *grad_value,
+                           void *grad_offsets, void *grad_logits, const msda_dims *dims, int dtype, unsigned flags,
+                           void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/*
+ * Decoder-layer epilogue -- SURVEY.md section 8f-2.  Replaces, after each attention / FFN block of
+ * DeformableTransformerDecoderLayer (models/detection/det_module.py:316-318, 331-333, 337-339),
+ *     tgt = tgt + dropout(tgt2);  tgt = norm(tgt)          (nn.Dropout + add + nn.LayerNorm: 3 launches, 5 in backward)
+ * with one kernel each way.  All tensors fp32, rows x channels contiguous, channels in {128, 256, 384, 512}:
+ *   forward : y = LayerNorm(x + keep * keep_scale * z) * gamma + beta.   keep: rows x channels bytes (non-zero = kept),
+ *             NULL = dropout off (then keep_scale should be 1).  h_saved / mean / rstd (rows x channels, rows, rows) are
+ *             what backward needs; pass all three NULL for inference.
+ *   backward: grad_x, grad_z (rows x channels), grad_gamma, grad_beta (channels; deterministic two-stage reduction
+ *             through `workspace`, msda_add_dropout_ln_workspace_bytes bytes, 16-byte aligned).
+ */
+int msda_add_dropout_ln_supported(int64_t channels);
+size_t msda_add_dropout_ln_workspace_bytes(int64_t rows, int64_t channels);
+int msda_add_dropout_ln_forward(const void *x, const void *z, const unsigned char *keep, float keep_scale,
+                                const void *gamma, const void *beta, float eps, void *y, void *h_saved, void *mean,
+                                void *rstd, int64_t rows, int64_t channels, void *cuda_stream);
+int msda_add_dropout_ln_backward(const void *grad_y, const void *h_saved, const void *mean, const void *rstd,
+                                 const unsigned char *keep, float keep_scale, const void *gamma, void *grad_x,
+                                 void *grad_z, void *grad_gamma, void *grad_beta, void *workspace,
+                                 size_t workspace_bytes, int64_t rows, int64_t channels, void *cuda_stream);
 
 /*
  * Level packing -- SURVEY.md section 8f-3.  Replaces the flatten/transpose/cat of prepare_od_inputs

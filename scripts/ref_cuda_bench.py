@@ -1,5 +1,5 @@
 """GPU: time the REFERENCE's own CUDA kernels (baseline/_ref, built by baseline/build_ref_cuda.py) next to grit_b200 on a
-bench workload, and compare the two outputs element-wise at full size.  Writes gpurun_out/ref_cuda_<workload>.json.
+bench workload, and compare the two outputs element-wise at full size.  Writes gpurun_out/r2_ref_cuda_<workload>[_N<batch>].json.
 
     python scripts/ref_cuda_bench.py [--workload detr_encoder_800x1333] [--iters 10]
 """
@@ -49,8 +49,11 @@ def main():
     ap.add_argument("--workload", default="detr_encoder_800x1333")
     ap.add_argument("--loc-dist", default="uniform")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=None, help="override the workload's images per GPU")
     args = ap.parse_args()
     cfg = dict(bench.WORKLOADS[args.workload])
+    if args.batch:
+        cfg["N"] = args.batch
     if cfg["dtype"] != "f32":
         cfg["dtype"] = "f32"  # the reference kernels are float/double only
     dev = torch.device("cuda:0")
@@ -94,7 +97,8 @@ def main():
            "speedup_fwd_bwd": (t["ref_fwd_ms"] + t["ref_bwd_ms"]) / (t["b200_fwd_ms"] + t["b200_bwd_ms"]),
            "kernels": [kf, kb], "max_norm_diff_vs_reference_kernel": agree}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", f"ref_cuda_{args.workload}.json"), "w") as f:
+    tag = f"_N{args.batch}" if args.batch else ""
+    with open(os.path.join(ROOT, "gpurun_out", f"r2_ref_cuda_{args.workload}{tag}.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res))
 

@@ -163,6 +163,7 @@ KERNEL_VARIANTS = [  # (msda_set_tuning settings, expected forward-kernel prefix
     ({"variant": 3, "v3_threads": 512, "bwd_mode": 2}, "fwd_staged", "+binned"),
     ({"variant": 3, "v3_threads": 1024, "bwd_mode": 3}, "fwd_staged", "+owned"),
     ({"variant": 3, "v3_threads": 768, "bwd_mode": 0}, "fwd_staged", "bwd_v5"),
+    ({"variant": 0, "staged_min_rows": 1, "bwd_mode": 0, "bin_min_rows": 64}, "fwd_", "bwd_v5"),
 ]
 
 
