@@ -89,6 +89,11 @@ def load():
         lib.msda_pack_levels.restype = ctypes.c_int
         lib.msda_pack_levels.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64), ctypes.c_int,
                                          ctypes.c_int64, ctypes.c_int64, vp, ctypes.c_int, ctypes.c_int, vp]
+        lib.msda_pack_levels_groupnorm.restype = ctypes.c_int
+        lib.msda_pack_levels_groupnorm.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                                   ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                                   ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                                   ctypes.c_float, vp, ctypes.c_int, vp, vp]
         lib.msda_probe_ceiling.restype = ctypes.c_int
         lib.msda_probe_ceiling.argtypes = [ctypes.c_int, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int64), vp]
         lib.msda_fused_supported.restype = ctypes.c_int
@@ -284,6 +289,34 @@ def pack_levels(levels, memory=None, unpack: bool = False):
     if rc:
         _raise(lib, rc, "msda_pack_levels")
     return memory
+
+
+def pack_levels_groupnorm(levels, weights, biases, num_groups, eps, out_dtype=torch.float32):
+    """levels: contiguous CUDA fp32 (N, C, H_l, W_l) conv outputs; weights / biases: each level's GroupNorm affine (C,).
+    -> (memory (N, S, C) of out_dtype, stats (L, N, G, 2) fp32 = mean, rstd)."""
+    lib = load()
+    n, c = levels[0].shape[:2]
+    hw = [int(t.shape[2] * t.shape[3]) for t in levels]
+    for t, w, b in zip(levels, weights, biases):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32 and tuple(t.shape[:2]) == (n, c)):
+            raise RuntimeError("pack_levels_groupnorm expects contiguous CUDA fp32 (N, C, H, W) tensors")
+        for p in (w, b):
+            if not (p.is_cuda and p.is_contiguous() and p.dtype == torch.float32 and tuple(p.shape) == (c,) and
+                    p.device == t.device):
+                raise RuntimeError("GroupNorm weight / bias must be contiguous CUDA fp32 (C,) tensors")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"pack_levels_groupnorm writes fp32 or bf16 memory, not {out_dtype}")
+    memory = torch.empty((n, sum(hw), c), dtype=out_dtype, device=levels[0].device)
+    stats = torch.empty((len(levels), n, num_groups, 2), dtype=torch.float32, device=levels[0].device)
+    arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    hws = (ctypes.c_int64 * len(levels))(*hw)
+    with torch.cuda.device(memory.device):
+        rc = lib.msda_pack_levels_groupnorm(arr(levels), hws, len(levels), n, c, int(num_groups), arr(weights),
+                                            arr(biases), float(eps), _ptr(memory), _DTYPE_CODE[out_dtype], _ptr(stats),
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc:
+        _raise(lib, rc, "msda_pack_levels_groupnorm")
+    return memory, stats
 
 
 def probe_ceiling(which: str, scratch, iters: int = 5):

@@ -79,7 +79,9 @@ std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 10
 std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
-std::atomic<int> g_staged_min_rows{600};  // auto: staged forward (fp32, D=32) when num_heads*num_query / #SMs >= this
+std::atomic<int> g_staged_rows{1024};     // staged forward: query rows per work item (CTA)
+std::atomic<int> g_staged_persistent{0};  // staged forward A/B: 1 = one CTA per SM walking the items round-robin
+std::atomic<int> g_staged_min_rows{200};  // auto: staged forward (D=32) when num_heads*num_query / #SMs >= this
 std::atomic<int> g_bin_min_rows{0};      // auto: binned coarse levels when num_query >= this; 0 = never (measured slower
                                          // than the plain row kernel on B200)
 std::atomic<int> g_owned_max_taps{4};    // auto: owned when taps per value pixel (Lq*L*P*4 / S) <= this
@@ -293,9 +295,19 @@ int fwd_staged_launch(const msda_dims *d, const void *value, const int64_t *shap
     const int smem = device_info().max_smem_optin - 1024;  // leave room for the kernel's static shared memory
     if (smem <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
     if (int rc = optin_smem(kernel, smem)) return rc;
-    kernel<<<device_info().sms, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc,
-                                                (const float *)attn, (T *)out, (int)d->batch, (int)d->spatial_size,
-                                                (int)d->num_heads, (int)d->num_query, smem / (int)sizeof(T));
+    // items = batch x chunks x heads, ~1024 rows each: small enough that the block scheduler's granularity costs little
+    // when it balances SMs of unequal speed (a grid of only ~4 items per SM loses up to a fifth to wave quantisation),
+    // large enough that staging the planes (one 169 KB read of the coarse levels per item) stays at a few percent
+    int rows_per_item = g_staged_rows.load();
+    if (rows_per_item < 64) rows_per_item = 64;
+    int64_t chunks = (d->num_query + rows_per_item - 1) / rows_per_item;
+    if (chunks < 1) chunks = 1;
+    const int64_t items = d->batch * chunks * d->num_heads;
+    if (items > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
+    const int64_t grid = g_staged_persistent.load() && items > device_info().sms ? device_info().sms : items;
+    kernel<<<(unsigned)grid, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+                                             (T *)out, (int)d->batch, (int)d->spatial_size, (int)d->num_heads,
+                                             (int)d->num_query, smem / (int)sizeof(T), (int)chunks);
     snprintf(tl_kernel, sizeof(tl_kernel), "fwd_staged<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
     return MSDA_OK;
 }
@@ -501,6 +513,8 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
     if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
     if (key && !strcmp(key, "staged_min_rows")) knob = &g_staged_min_rows;
+    if (key && !strcmp(key, "staged_rows")) knob = &g_staged_rows;
+    if (key && !strcmp(key, "staged_persistent")) knob = &g_staged_persistent;
     if (key && !strcmp(key, "owned_max_taps")) knob = &g_owned_max_taps;
     if (!knob) return -1;
     return knob->exchange(value);
@@ -530,10 +544,11 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        // The staged forward pays off when every persistent CTA sees enough rows per staged (image, head) plane and the
-        // taps are full 128-byte lines (fp32, D=32): measured 1.40 vs 1.47 ms at 800x1333, slower at 384x640 and in bf16.
+        // The staged forward pays off when two coarse levels of a head fit in shared memory (D=32) and there are enough
+        // rows to amortise staging them: measured (profiles/r02_staged_ab.txt) 1.34 vs 1.47 ms at 800x1333 fp32, 0.60 vs
+        // 0.69 ms at 384x640 fp32, 2.80 vs 2.97 ms at 800x1333 bf16; slower at D=64 (only the coarsest level fits).
         const int variant = g_variant.load();
-        const bool staged_auto = variant == 0 && dtype == MSDA_F32 && dims->channels == 32 &&
+        const bool staged_auto = variant == 0 && dims->channels == 32 &&
                                  dims->num_heads * dims->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms;
         if (variant == 3 || staged_auto) {
             const int rc = dtype == MSDA_F32
@@ -1139,6 +1154,52 @@ int msda_add_dropout_ln_backward(const void *grad_y, const void *h_saved, const 
     tl_launches += 2;
     snprintf(tl_kernel, sizeof(tl_kernel), "add_dropout_ln_bwd<C%d>", (int)channels);
     return check_cuda(cudaPeekAtLastError(), "msda_add_dropout_ln_backward launch");
+}
+
+// ---- GroupNorm epilogue -> packed memory (msda_kernels_layer.cuh) ---------------------------------------------------------
+int msda_pack_levels_groupnorm(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch,
+                               int64_t channels, int num_groups, void *const *gamma_ptrs, void *const *beta_ptrs, float eps,
+                               void *memory, int out_dtype, void *stats, void *cuda_stream)
+{
+    tl_error[0] = 0;
+    if (!level_ptrs || !level_hw || !gamma_ptrs || !beta_ptrs || !memory || !stats)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "null pointer");
+    if (num_levels < 1 || num_levels > 8) return fail(MSDA_ERR_UNSUPPORTED, "msda_pack_levels_groupnorm supports 1..8 levels");
+    if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "memory dtype must be f32 or bf16");
+    if (num_groups <= 0 || channels <= 0 || channels % num_groups != 0)
+        return fail(MSDA_ERR_INVALID_ARGUMENT, "channels must be a positive multiple of num_groups");
+    if (batch <= 0) return MSDA_OK;
+    if (batch > 65535 || num_groups > 65535) return fail(MSDA_ERR_UNSUPPORTED, "batch / num_groups > 65535");
+    msda::GnPackArgs a;
+    a.num_levels = num_levels;
+    int64_t S = 0, tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+        if (!level_ptrs[l] || !gamma_ptrs[l] || !beta_ptrs[l] || level_hw[l] <= 0 || level_hw[l] > 0x7fffffff)
+            return fail(MSDA_ERR_INVALID_ARGUMENT, "bad level %d", l);
+        a.level[l] = (const float *)level_ptrs[l];
+        a.gamma[l] = (const float *)gamma_ptrs[l], a.beta[l] = (const float *)beta_ptrs[l];
+        a.hw[l] = (int)level_hw[l];
+        a.start[l] = (int)S;
+        a.tile_start[l] = (int)tiles;
+        S += level_hw[l];
+        tiles += (level_hw[l] + 31) / 32;
+    }
+    a.tile_start[num_levels] = (int)tiles;
+    if (S > 0x7fffffff || tiles > 0x7fffffff) return fail(MSDA_ERR_INVALID_ARGUMENT, "pyramid too large");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    msda::msda_gn_stats<<<dim3((unsigned)num_groups, (unsigned)batch, (unsigned)num_levels), 256, 0, st>>>(
+        a, (int)batch, (int)channels, num_groups, eps, (float *)stats);
+    const dim3 grid((unsigned)tiles, (unsigned)((channels + 31) / 32), (unsigned)batch);
+    if (out_dtype == MSDA_F32)
+        msda::msda_pack_levels_gn<float><<<grid, 256, 0, st>>>(a, (const float *)stats, (float *)memory, (int)batch,
+                                                               (int)channels, num_groups, (int)S);
+    else
+        msda::msda_pack_levels_gn<__nv_bfloat16><<<grid, 256, 0, st>>>(a, (const float *)stats, (__nv_bfloat16 *)memory,
+                                                                       (int)batch, (int)channels, num_groups, (int)S);
+    tl_launches += 2;
+    snprintf(tl_kernel, sizeof(tl_kernel), "pack_levels_gn<%s>", dtype_name(out_dtype));
+    return check_cuda(cudaPeekAtLastError(), "msda_pack_levels_groupnorm launch");
 }
 
 // ---- host-buffer session ---------------------------------------------------------------------------

@@ -112,6 +112,22 @@ __device__ __forceinline__ void red_add_chunk(float *p, const float (&g)[E], flo
     for (int i = 0; i < E; i += 4) red_add_f32x4(p + i, s * g[i], s * g[i + 1], s * g[i + 2], s * g[i + 3]);
 }
 
+// Hide how a pointer was computed from the optimiser.  The row kernels add a 32-bit element offset per tap to a per-lane
+// base pointer; when ptxas can see that the base ends in `+ lane_chunk` it re-derives every tap address from scratch
+// (LOP3 + SHF + LEA + LEA.HI.X per tap).  With an opaque base each tap address is one IMAD.WIDE.
+template <typename T>
+__device__ __forceinline__ const T *opaque_ptr(const T *p)
+{
+    asm("" : "+l"(p));
+    return p;
+}
+template <typename T>
+__device__ __forceinline__ T *opaque_ptr(T *p)
+{
+    asm("" : "+l"(p));
+    return p;
+}
+
 // One sample point resolved against its level: tap offsets (in pixels), validity and weights.
 struct Taps {
     int pix;          // start + r0*W + c0  (pixel index of the top-left tap inside the image)

@@ -17,6 +17,7 @@
 // Statistics are computed in fp32 in two passes over registers (mean first, then the centred second moment).
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -158,6 +159,99 @@ __global__ void msda_ln_param_grads(const float *__restrict__ partial, int block
     }
     dgamma[c] = a;
     dbeta[c] = b;
+}
+
+// ---- GroupNorm epilogue -> packed memory ----------------------------------------------------------------
+// Detector.input_proj (models/detection/detector.py:39-44, 64) is Conv2d(1x1) + GroupNorm(32, C) per level, and
+// prepare_od_inputs (det_module.py:146-155) then flattens / transposes / concatenates the normalised NCHW maps into the
+// (N, S, C) memory the op reads: GroupNorm writes N*C*H*W, the re-layout reads and writes it again.  Here the
+// GroupNorm epilogue writes the memory layout directly (optionally as bf16): msda_gn_stats computes mean / rstd per
+// (level, image, group) from the conv output, msda_pack_levels_gn normalises, applies the affine and transposes through
+// a shared-memory tile in one pass.
+struct GnPackArgs {
+    const float *level[8];   // conv outputs, NCHW fp32
+    const float *gamma[8];   // GroupNorm weight / bias of each level's input_proj
+    const float *beta[8];
+    int hw[8];
+    int start[8];
+    int tile_start[9];
+    int num_levels;
+};
+
+// stats: (L, N, G, 2) = mean, rstd.  One CTA per (group, image, level); a group's channels are contiguous in NCHW.
+__global__ void __launch_bounds__(256)
+msda_gn_stats(GnPackArgs args, int N, int C, int G, float eps, float *__restrict__ stats)
+{
+    const int g = blockIdx.x, n = blockIdx.y, l = blockIdx.z;
+    const int cpg = C / G, hw = args.hw[l];
+    const int64_t m = (int64_t)cpg * hw;
+    const float *x = args.level[l] + ((int64_t)n * C + (int64_t)g * cpg) * hw;
+    const float shift = m > 0 ? __ldg(x) : 0.f;  // shifted sums: stable when |mean| >> std
+    float s = 0.f, ss = 0.f;
+    for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+        const float d = __ldg(x + i) - shift;
+        s += d;
+        ss = fmaf(d, d, ss);
+    }
+    __shared__ float red[2][8];
+    s = warp_sum(s), ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s, red[1][threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) a += red[0][w], b += red[1][w];
+        const float inv = m > 0 ? 1.f / (float)m : 0.f;
+        const float mu = a * inv;
+        const float var = fmaxf(b * inv - mu * mu, 0.f);
+        float *o = stats + (((int64_t)l * N + n) * G + g) * 2;
+        o[0] = shift + mu;
+        o[1] = rsqrtf(var + eps);
+    }
+}
+
+template <typename TOUT>
+__device__ __forceinline__ TOUT gn_cast(float v);
+template <>
+__device__ __forceinline__ float gn_cast<float>(float v)
+{
+    return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 gn_cast<__nv_bfloat16>(float v)
+{
+    return __float2bfloat16_rn(v);
+}
+
+template <typename TOUT>
+__global__ void __launch_bounds__(256)
+msda_pack_levels_gn(GnPackArgs args, const float *__restrict__ stats, TOUT *__restrict__ memory, int N, int C, int G, int S)
+{
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int c0 = blockIdx.y * 32;
+    int l = 0;
+    while (l + 1 < args.num_levels && (int)blockIdx.x >= args.tile_start[l + 1]) ++l;
+    const int p0 = ((int)blockIdx.x - args.tile_start[l]) * 32;
+    const int hw = args.hw[l], cpg = C / G;
+    const float *lvl = args.level[l] + (int64_t)n * C * hw;
+    TOUT *mem = memory + ((int64_t)n * S + args.start[l]) * C;
+    const float *st = stats + ((int64_t)l * N + n) * G * 2;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {  // read (c, p) with p fastest, normalise
+        const int c = c0 + ty + j, p = p0 + tx;
+        if (c < C && p < hw) {
+            const float mu = __ldg(st + (c / cpg) * 2), rs = __ldg(st + (c / cpg) * 2 + 1);
+            tile[ty + j][tx] = fmaf((__ldg(lvl + (int64_t)c * hw + p) - mu) * rs, __ldg(args.gamma[l] + c),
+                                    __ldg(args.beta[l] + c));
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {  // write (p, c) with c fastest
+        const int p = p0 + ty + j, c = c0 + tx;
+        if (c < C && p < hw) mem[(int64_t)p * C + c] = gn_cast<TOUT>(tile[tx][ty + j]);
+    }
 }
 
 }  // namespace msda

@@ -1,21 +1,21 @@
-// msda_kernels_staged.cuh -- persistent, shared-memory-staged forward for large query counts (sm_100a).
+// msda_kernels_staged.cuh -- shared-memory-staged forward for large query counts (sm_100a).
 //
-// Why: the first two kernel generations are bound by the SM <-> L2 crossbar, not by HBM
-// (profiles/r01_*.txt): every bilinear tap is a 128-byte line that misses L1, and in the backward
-// every tap is a 128-byte `red` that has to leave the SM (L1->XBAR request path 90 % busy).
-// The coarse pyramid levels of ONE (image, head) pair are tiny, though -- at 800x1333 levels 2+3
-// are 1323 pixels = 169 KB in fp32 -- and receive half of all taps.  So:
+// Why: every bilinear tap of the row kernel (msda_kernels_v5.cuh) is a 128-byte line that misses L1 and comes from
+// L2.  The coarse pyramid levels of ONE (image, head) pair are tiny, though -- at 800x1333 levels 2+3 are 1323 pixels =
+// 169 KB in fp32 -- and receive half of all taps, and shared memory serves random 128-byte lines 1.8x faster than L2
+// (profiles/r02_micro_gather_paths.txt: 284 vs 162 G lines/s).  So:
 //
-//   * one persistent CTA per SM; the CTAs sweep the batch one image at a time (keeps the image's
-//     value maps L2-resident), each CTA owning a contiguous slice of the image's (head, query)
-//     rows in head-major order, i.e. at most two (image, head) segments per image;
-//   * per segment the CTA stages the head's coarse-level planes in shared memory
-//       forward : the VALUE planes  -> taps on staged levels are LDS.128, not L2 round trips;
-//       backward: fp32 grad_value ACCUMULATORS -> taps on staged levels are shared-memory atomics,
-//                 flushed with one vector `red` per pixel when the segment ends;
-//     which levels fit is decided on the device from spatial_shapes (no host sync): greedy from
-//     the smallest plane up, within the dynamic shared-memory budget passed at launch;
-//   * rows are processed exactly like v2 (warp per row, resolve once, lane group per tap).
+//   * a work item is (image, head, chunk of the queries); one 1024-thread CTA per item stages that head's coarse-level
+//     value planes in shared memory (which levels fit is decided on the device from spatial_shapes -- no host sync --
+//     greedy from the smallest plane up, within the dynamic shared-memory budget passed at launch) and then walks the
+//     chunk's rows exactly like the row kernel (warp per row, resolve once, lane group per tap): taps on staged levels
+//     are LDS.128, the others L2 round trips;
+//   * items are ordinary CTAs of a grid several times larger than the machine (images outermost, so the CTAs in flight
+//     work on a few images whose maps stay L2-resident): the hardware block scheduler hands them out as SMs free up.
+//     The first version of this kernel (round 1) was persistent with a static slice of the rows per SM; B200's SMs do
+//     not run at one speed (two dies, per-GPU SM -> L2 distance map), so static slices left a tail that made the kernel
+//     slower than the row kernel on some boxes (1.53 vs 1.47 ms) and faster on others (1.34 ms).  Staging costs 169 KB
+//     of L2 reads per item against ~4 500 rows x 8 KB of taps (< 1 %).
 #pragma once
 
 #include "msda_common.cuh"
@@ -68,14 +68,6 @@ __device__ __forceinline__ void plan_levels(const int64_t *shapes, const int64_t
     __syncthreads();
 }
 
-// Row range of CTA `c` inside one image, in head-major order (row index = m*Lq + q).
-__device__ __forceinline__ void cta_slice(int c, int nctas, int M, int Lq, int &lo, int &hi)
-{
-    const long long R = (long long)M * Lq;
-    lo = (int)(R * c / nctas);
-    hi = (int)(R * (c + 1) / nctas);
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -83,7 +75,7 @@ template <typename T, int D, int L, int P, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int N, int S, int M,
-            int Lq, int budget_elems)
+            int Lq, int budget_elems, int chunks)
 {
     constexpr int E = Chunk<T>::E;
     constexpr int LPT = D / E;
@@ -101,16 +93,22 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPT, sub = lane % LPT;
     const int MD = M * D;
-    int lo, hi;
-    cta_slice(blockIdx.x, gridDim.x, M, Lq, lo, hi);
-    if (lo >= hi) return;
     const int rp = lane % LP, rl = rp / P;
     const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
 
-    for (int b = 0; b < N; ++b) {
-        for (int m = lo / Lq; m <= (hi - 1) / Lq; ++m) {
-            const int q0 = max(lo - m * Lq, 0), q1 = min(hi - m * Lq, Lq);
+    // item = (image, chunk, head), head fastest: item = (b * chunks + c) * M + m.  The grid normally has one CTA per
+    // item (dynamic scheduling by the hardware); a smaller grid walks the items round-robin (A/B knob "staged_persistent").
+    const unsigned n_items = (unsigned)N * (unsigned)chunks * (unsigned)M;
+    for (unsigned item = blockIdx.x; item < n_items; item += gridDim.x) {
+        {
+            const int m = (int)(item % (unsigned)M);
+            const int c = (int)((item / (unsigned)M) % (unsigned)chunks);
+            const int b = (int)(item / ((unsigned)M * (unsigned)chunks));
+            const int per = (Lq + chunks - 1) / chunks;
+            const int q0 = c * per, q1 = min(q0 + per, Lq);
+            if (q0 >= q1) continue;
             const T *vimg = value + ((int64_t)b * S * M + m) * D;
+            const T *vlane = opaque_ptr(vimg + sub * E);  // per-lane base of the L2 taps: one IMAD.WIDE per address
 
             // ---- stage this head's coarse planes ---------------------------------------------------
             __syncthreads();  // previous segment's readers are done
@@ -181,19 +179,19 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
                             if (pm & 8) Chunk<T>::load_shared(s0 + so3, v3);
                         }
                     } else {  // taps from L2: one IMAD.WIDE per address
-                        const int o0 = pix * MD + sub * E, o1 = o0 + MD, o2 = o0 + W * MD, o3 = o2 + MD;
+                        const int o0 = pix * MD, o1 = o0 + MD, o2 = o0 + W * MD, o3 = o2 + MD;
                         if (all_valid) {
-                            Chunk<T>::load(vimg + o0, v0);
-                            Chunk<T>::load(vimg + o1, v1);
-                            Chunk<T>::load(vimg + o2, v2);
-                            Chunk<T>::load(vimg + o3, v3);
+                            Chunk<T>::load(vlane + o0, v0);
+                            Chunk<T>::load(vlane + o1, v1);
+                            Chunk<T>::load(vlane + o2, v2);
+                            Chunk<T>::load(vlane + o3, v3);
                         } else {
 #pragma unroll
                             for (int e = 0; e < E; ++e) v0[e] = v1[e] = v2[e] = v3[e] = 0.f;
-                            if (pm & 1) Chunk<T>::load(vimg + o0, v0);
-                            if (pm & 2) Chunk<T>::load(vimg + o1, v1);
-                            if (pm & 4) Chunk<T>::load(vimg + o2, v2);
-                            if (pm & 8) Chunk<T>::load(vimg + o3, v3);
+                            if (pm & 1) Chunk<T>::load(vlane + o0, v0);
+                            if (pm & 2) Chunk<T>::load(vlane + o1, v1);
+                            if (pm & 4) Chunk<T>::load(vlane + o2, v2);
+                            if (pm & 8) Chunk<T>::load(vlane + o3, v3);
                         }
                     }
                     const float ah = a - a * lh, al = a * lh, hw = 1.f - lw;

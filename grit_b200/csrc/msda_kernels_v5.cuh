@@ -201,7 +201,7 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     const unsigned m = ((M & (M - 1)) == 0) ? (r & (unsigned)(M - 1)) : (r % (unsigned)M);
     const int MD = M * D;
     const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
-    const T *vimg = value + ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
+    const T *vimg = opaque_ptr(value + ((int64_t)blockIdx.y * S * M + m) * D + sub * E);
 
     const int rp = lane % LP;
     const int rl = rp / P;
@@ -328,8 +328,8 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     const int MD = M * D;
     const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
     const int64_t img = ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
-    const T *vimg = value + img;
-    typename ACC::elem *gimg = gv_acc + img;
+    const T *vimg = opaque_ptr(value + img);
+    typename ACC::elem *gimg = opaque_ptr(gv_acc + img);
     ACC accp;
     if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
     accp.template prepare<T, E>(grad_out + row * D, sub, LPT);
@@ -425,12 +425,21 @@ __device__ __forceinline__ unsigned probe_hash(unsigned x)
     return x;
 }
 
+// Index generation must not be what the probe measures: one LCG step + one multiply-high per line (3 instructions),
+// instead of a hash and a runtime modulo (~40 instructions, which made the round-1 probes issue-bound at ~56 B/clk/SM).
+__device__ __forceinline__ unsigned probe_next(unsigned &state, unsigned n_lines)
+{
+    state = state * 1664525u + 1013904223u;
+    return __umulhi(state, n_lines);
+}
+
 __global__ void msda_probe_red(float *dst, unsigned n_lines, int iters)
 {
     const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
     const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned state = probe_hash(w * 4u + g);
     for (int it = 0; it < iters; ++it) {
-        const unsigned line = probe_hash(w * 9781u + it * 4u + g) % n_lines;
+        const unsigned line = probe_next(state, n_lines);
         red_add_f32x4(dst + (size_t)line * 32 + sub * 4, 1.f, 2.f, 3.f, 4.f);
     }
 }
@@ -439,12 +448,13 @@ __global__ void msda_probe_gather(const float *__restrict__ src, float *out, uns
 {
     const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
     const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    unsigned state = probe_hash(w * 4u + g);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int it = 0; it < iters; it += 16) {
         float4 v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            const unsigned line = probe_hash(w * 9781u + (it + k) * 4u + g) % n_lines;
+            const unsigned line = probe_next(state, n_lines);
             v[k] = __ldg(reinterpret_cast<const float4 *>(src + (size_t)line * 32 + sub * 4));
         }
 #pragma unroll

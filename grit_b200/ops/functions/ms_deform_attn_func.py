@@ -226,6 +226,63 @@ class PackLevelsFunction(Function):
         return tuple(grads)
 
 
+class PackLevelsGroupNormFunction(Function):
+    """GroupNorm + re-layout in one pass (second half): the conv outputs of Detector.input_proj
+    (models/detection/detector.py:39-44, 64) go straight to the (N, S, C) memory the op reads, normalised with each
+    level's GroupNorm affine, optionally as bf16 -- instead of GroupNorm writing N*C*H*W and prepare_od_inputs
+    (det_module.py:146-155) reading and writing it again.  Backward: the packing's adjoint (msda_pack_levels, unpack)
+    followed by torch's own GroupNorm backward on the statistics saved here."""
+
+    @staticmethod
+    def forward(ctx, num_groups, eps, out_dtype, n_levels, *tensors):
+        levels = [t.contiguous() for t in tensors[:n_levels]]
+        weights = [t.contiguous() for t in tensors[n_levels:2 * n_levels]]
+        biases = [t.contiguous() for t in tensors[2 * n_levels:]]
+        memory, stats = _lib.pack_levels_groupnorm(levels, weights, biases, num_groups, eps, out_dtype)
+        ctx.num_groups, ctx.n_levels = num_groups, n_levels
+        ctx.save_for_backward(stats, *levels, *weights)
+        return memory
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_memory):
+        stats = ctx.saved_tensors[0]
+        levels = ctx.saved_tensors[1:1 + ctx.n_levels]
+        weights = ctx.saved_tensors[1 + ctx.n_levels:]
+        grads = [torch.empty(t.shape, dtype=torch.float32, device=t.device) for t in levels]
+        _lib.pack_levels(grads, grad_memory.float().contiguous(), unpack=True)
+        g_levels, g_weights, g_biases = [], [], []
+        for l, (x, w, dy) in enumerate(zip(levels, weights, grads)):
+            n, c, h, wd = x.shape
+            mean, rstd = stats[l, :, :, 0].contiguous(), stats[l, :, :, 1].contiguous()
+            gx, gw, gb = torch.ops.aten.native_group_norm_backward(dy, x, mean, rstd, w, n, c, h * wd, ctx.num_groups,
+                                                                   [True, True, True])
+            g_levels.append(gx), g_weights.append(gw), g_biases.append(gb)
+        return (None, None, None, None, *g_levels, *g_weights, *g_biases)
+
+
+def pack_levels_groupnorm(conv_outputs, group_norms, out_dtype=None):
+    """``memory, spatial_shapes, level_start_index`` from the per-level CONV outputs (N, C, H_l, W_l) and the
+    ``nn.GroupNorm`` modules that follow them in Detector.input_proj -- equals
+    ``torch.cat([gn(x).flatten(2).transpose(1, 2) for x, gn in zip(conv_outputs, group_norms)], 1)`` in fp32 (or rounded
+    to ``out_dtype`` = torch.bfloat16)."""
+    gn0 = group_norms[0]
+    for gn in group_norms:
+        if gn.num_groups != gn0.num_groups or gn.eps != gn0.eps or gn.weight is None or gn.bias is None:
+            raise RuntimeError("pack_levels_groupnorm needs affine GroupNorms with the same num_groups / eps on every level")
+    n_levels = len(conv_outputs)
+    memory = PackLevelsGroupNormFunction.apply(gn0.num_groups, gn0.eps, out_dtype or torch.float32, n_levels,
+                                               *[x.float() for x in conv_outputs], *[gn.weight for gn in group_norms],
+                                               *[gn.bias for gn in group_norms])
+    hw = [(int(t.shape[2]), int(t.shape[3])) for t in conv_outputs]
+    spatial_shapes = torch.as_tensor(hw, dtype=torch.long, device=memory.device)
+    starts = [0]
+    for h, w in hw[:-1]:
+        starts.append(starts[-1] + h * w)
+    level_start_index = torch.as_tensor(starts, dtype=torch.long, device=memory.device)
+    return memory, spatial_shapes, level_start_index
+
+
 def pack_levels(levels):
     """``memory, spatial_shapes, level_start_index`` from a list of (N, C, H_l, W_l) feature maps -- the tensors
     prepare_od_inputs builds (models/detection/det_module.py:146-158); shapes/starts are int64 tensors on the device."""

@@ -92,16 +92,18 @@ const char *msda_last_kernel(void);
 int64_t msda_launch_count(int reset);
 
 /* Tuning / A-B testing knob (process-wide; for benchmarks and tests).  Keys:
- *   "variant"        forward: 0 auto (default: the staged forward for fp32 D=32 problems with >= "staged_min_rows"
- *                    (image, head, query) rows per SM, else the row kernel) | 5 lean row kernel | 3 persistent
- *                    shared-memory-staged forward
+ *   "variant"        forward: 0 auto (default: the staged forward for D=32 problems with >= "staged_min_rows"
+ *                    (head, query) rows per image per SM, else the row kernel) | 5 lean row kernel |
+ *                    3 shared-memory-staged forward
  *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
  *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
  *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
  *                    2 row kernel + on-SM aggregation of the coarse levels (msda_bwd_binned) |
  *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems)
- *   "staged_min_rows" see "variant"   (default 600)
+ *   "staged_min_rows" see "variant"   (default 200)
+ *   "staged_rows"    staged forward: query rows per work item / CTA (default 1024)
+ *   "staged_persistent" staged forward A/B: 1 = one CTA per SM walking the items round-robin instead of one CTA per item
  *   "bin_min_rows"   auto rule: mode 2 when num_query >= this; 0 = never (default: measured slower than mode 1 on B200)
  *   "owned_max_taps" auto rule: mode 3 for bf16 problems with num_query*L*P*4 <= this * spatial_size (default 4) and a
  *                    grad_value of at least 64 MB (for fp32 both strategies write grad_value once and measure the same)
@@ -201,6 +203,18 @@ int msda_add_dropout_ln_backward(const void *grad_y, const void *h_saved, const 
  */
 int msda_pack_levels(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch, int64_t channels,
                      void *memory, int dtype, int unpack, void *cuda_stream);
+
+/*
+ * GroupNorm epilogue -> packed memory -- SURVEY.md section 8f-3, second half.  Detector.input_proj
+ * (models/detection/detector.py:39-44, 64) ends in GroupNorm(num_groups, C) on each level's conv output, and
+ * prepare_od_inputs then re-lays the normalised maps out as memory.  This call does both: `level_ptrs[l]` is the fp32 NCHW
+ * CONV output of level l (pre-normalisation), gamma/beta the level's GroupNorm affine (fp32, C each); `memory`
+ * (N, sum_l H_l*W_l, C) receives GroupNorm(x) in the op's layout as f32 or bf16 (out_dtype); `stats` (L, N, G, 2) fp32
+ * receives mean / rstd (what a GroupNorm backward needs).  Two launches: statistics, then normalise + affine + transpose.
+ */
+int msda_pack_levels_groupnorm(void *const *level_ptrs, const int64_t *level_hw, int num_levels, int64_t batch,
+                               int64_t channels, int num_groups, void *const *gamma_ptrs, void *const *beta_ptrs, float eps,
+                               void *memory, int out_dtype, void *stats, void *cuda_stream);
 
 /*
  * Measurement aid for bench.py: one launch of a microbenchmark with the kernels' access pattern and none of their

@@ -28,13 +28,16 @@ from grit_b200 import _lib  # noqa: E402
 
 def set_window(stream_handle, ptr, nbytes, hit_ratio):
     from cuda import cudart
-    attr = cudart.cudaStreamAttrValue()
+    attr = getattr(cudart, "cudaStreamAttrValue", None) or cudart.cudaLaunchAttributeValue
+    attr = attr()
     attr.accessPolicyWindow.base_ptr = ptr
     attr.accessPolicyWindow.num_bytes = nbytes
     attr.accessPolicyWindow.hitRatio = hit_ratio
     attr.accessPolicyWindow.hitProp = cudart.cudaAccessProperty.cudaAccessPropertyPersisting
     attr.accessPolicyWindow.missProp = cudart.cudaAccessProperty.cudaAccessPropertyStreaming
-    err, = cudart.cudaStreamSetAttribute(stream_handle, cudart.cudaStreamAttrID.cudaStreamAttributeAccessPolicyWindow, attr)
+    ids = cudart.cudaStreamAttrID
+    attr_id = getattr(ids, "cudaStreamAttributeAccessPolicyWindow", None) or ids.cudaLaunchAttributeAccessPolicyWindow
+    err, = cudart.cudaStreamSetAttribute(stream_handle, attr_id, attr)
     return int(err)
 
 

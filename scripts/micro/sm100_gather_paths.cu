@@ -38,6 +38,13 @@ __device__ __forceinline__ unsigned hash32(unsigned x)
     return x;
 }
 
+// index generation must not be what is measured: one LCG step + one multiply-high per line
+__device__ __forceinline__ unsigned next_line(unsigned &state, unsigned n)
+{
+    state = state * 1664525u + 1013904223u;
+    return __umulhi(state, n);
+}
+
 constexpr int kWarps = 8;
 
 __global__ void __launch_bounds__(kWarps * 32) k_ldg(const float4 *__restrict__ src, float *out, unsigned n_lines, int iters)
@@ -45,11 +52,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_ldg(const float4 *__restrict__ 
     const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
     const unsigned w = blockIdx.x * kWarps + (threadIdx.x >> 5);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned state = hash32(w * 4u + g);
     for (int it = 0; it < iters; it += 8) {
         float4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const unsigned line = hash32(w * 9781u + (it + k) * 4u + g) % n_lines;
+            const unsigned line = next_line(state, n_lines);
             v[k] = __ldg(src + (size_t)line * 8 + sub);
         }
 #pragma unroll
@@ -75,13 +83,13 @@ __global__ void __launch_bounds__(kWarps * 32) k_smem(float *out, unsigned lines
     const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
     const unsigned w = blockIdx.x * kWarps + (threadIdx.x >> 5);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned state = hash32(w * 4u + g);
     for (int it = 0; it < iters; it += 8) {
         float4 v[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const unsigned h = hash32(w * 9781u + (it + k) * 4u + g);
-            const unsigned line = (h >> 8) % lines_per_cta;
-            const float4 *base = REMOTE ? cluster.map_shared_rank(sm, h % nranks) : sm;
+            const unsigned line = next_line(state, lines_per_cta);
+            const float4 *base = REMOTE ? cluster.map_shared_rank(sm, (state >> 4) & (nranks - 1)) : sm;
             v[k] = base[(size_t)line * 8 + sub];
         }
 #pragma unroll
@@ -113,8 +121,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_gather4(const __grid_constant__
 
     auto issue = [&](int it, int d) {
         if (lane == 0) {
-            const unsigned h0 = hash32(w * 9781u + it * 4u + 0) % n_lines, h1 = hash32(w * 9781u + it * 4u + 1) % n_lines;
-            const unsigned h2 = hash32(w * 9781u + it * 4u + 2) % n_lines, h3 = hash32(w * 9781u + it * 4u + 3) % n_lines;
+            unsigned st = hash32(w * 9781u + it);
+            const unsigned h0 = next_line(st, n_lines), h1 = next_line(st, n_lines);
+            const unsigned h2 = next_line(st, n_lines), h3 = next_line(st, n_lines);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 512;" ::"r"(smem_u32(mybar + d)) : "memory");
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
@@ -189,11 +198,11 @@ int main()
         CK(cudaEventElapsedTime(&ms, e0, e1));
         report("ldg", (double)blocks * kWarps * iters * 4, ms, sms);
     }
-    const int smem_bytes = 160 * 1024;
+    const int smem_bytes = 64 * 1024;  // 512 lines per CTA; three CTAs (24 warps) per SM
     const unsigned lines_per_cta = smem_bytes / 128;
     {  // lds
         CK(cudaFuncSetAttribute(k_smem<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        const int blocks = sms;
+        const int blocks = sms * 3;
         for (int rep = 0; rep < 2; ++rep) {
             CK(cudaEventRecord(e0));
             k_smem<false><<<blocks, kWarps * 32, smem_bytes>>>(out, lines_per_cta, iters * 8);

@@ -226,3 +226,37 @@ def test_graphed_decoder_and_region_feature_extraction(lib):
     feats_eager = extract_region_features(layers, b["tgt"], b["query_pos"], b["reference_points"], b["src"], shapes, lsi,
                                           b["valid_ratios"], b["padding_mask"])
     assert max_norm_err(feats_eager.cpu().numpy(), eager_b.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,shapes_l", [(256, [(12, 20), (6, 10), (3, 5), (2, 3)]), (512, [(13, 21), (7, 11), (4, 6), (2, 3)])])
+def test_groupnorm_epilogue_writes_packed_memory(lib, out_dtype, C, shapes_l):
+    """GroupNorm(32, C) of every level's conv output written straight into the (N, S, C) memory layout
+    == the reference's GroupNorm (detector.py:39-44, 64) + flatten/transpose/cat (det_module.py:146-155), forward and
+    backward (gradients w.r.t. the conv outputs and every level's GroupNorm weight / bias)."""
+    from grit_b200 import pack_levels_groupnorm
+    torch.manual_seed(C)
+    N = 3
+    gns = [torch.nn.GroupNorm(32, C).cuda() for _ in shapes_l]
+    for gn in gns:
+        with torch.no_grad():
+            gn.weight.normal_(1.0, 0.3), gn.bias.normal_(0, 0.3)
+    xs = [(torch.randn(N, C, h, w, device="cuda") * 2 + 5).requires_grad_(True) for h, w in shapes_l]  # |mean| >> std
+    memory, spatial_shapes, lsi = pack_levels_groupnorm(xs, gns, out_dtype)
+    assert lib.last_kernel().startswith("pack_levels_gn")
+    ref = torch.cat([gn(x).flatten(2).transpose(1, 2) for x, gn in zip(xs, gns)], 1)
+    assert memory.dtype == out_dtype and tuple(memory.shape) == tuple(ref.shape)
+    assert spatial_shapes.tolist() == [list(s) for s in shapes_l] and int(lsi[1]) == shapes_l[0][0] * shapes_l[0][1]
+    tol = 1e-5 if out_dtype == torch.float32 else 1e-2
+    assert max_norm_err(memory.float().detach().cpu().numpy(), ref.detach().cpu().numpy()) < tol
+    g = torch.randn_like(ref)
+    memory.backward(g.to(out_dtype))
+    got = [x.grad.clone() for x in xs] + [gn.weight.grad.clone() for gn in gns] + [gn.bias.grad.clone() for gn in gns]
+    for x in xs:
+        x.grad = None
+    for gn in gns:
+        gn.zero_grad(set_to_none=True)
+    ref.backward(g.to(out_dtype).float())
+    want = [x.grad for x in xs] + [gn.weight.grad for gn in gns] + [gn.bias.grad for gn in gns]
+    for a, b in zip(got, want):
+        assert max_norm_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-4
