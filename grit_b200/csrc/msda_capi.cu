@@ -544,11 +544,14 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        // The staged forward pays off when two coarse levels of a head fit in shared memory (D=32) and there are enough
-        // rows to amortise staging them: measured (profiles/r02_staged_ab.txt) 1.34 vs 1.47 ms at 800x1333 fp32, 0.60 vs
-        // 0.69 ms at 384x640 fp32, 2.80 vs 2.97 ms at 800x1333 bf16; slower at D=64 (only the coarsest level fits).
+        // The staged forward pays off when at least three of the four levels of a head fit in shared memory, i.e. >= 3/4
+        // of the taps come from the SM (measured, profiles/r02_staged_ab.txt: 0.60 vs 0.62 ms at 384x640 fp32); with two
+        // levels on chip (800x1333: 1.34 vs 1.31 ms) or one (D=64) the row kernel wins.  The host does not read
+        // spatial_shapes, so the rule assumes the usual 4:1 pyramid: all levels but the finest hold ~S/4 pixels.
         const int variant = g_variant.load();
-        const bool staged_auto = variant == 0 && dims->channels == 32 &&
+        const int64_t coarse_bytes = dims->spatial_size / 4 * dims->channels * (int64_t)dtype_size(dtype);
+        const bool staged_auto = variant == 0 && dims->channels == 32 && dims->num_levels >= 3 &&
+                                 coarse_bytes <= device_info().max_smem_optin - 2048 &&
                                  dims->num_heads * dims->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms;
         if (variant == 3 || staged_auto) {
             const int rc = dtype == MSDA_F32

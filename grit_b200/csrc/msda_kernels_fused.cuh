@@ -163,8 +163,8 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const int64_t row = (int64_t)blockIdx.y * rows_per_image + r;
     const int64_t bq = (int64_t)blockIdx.y * Lq + q;
     const int64_t img = ((int64_t)blockIdx.y * S * M + m) * D + sub * E;
-    const T *vimg = opaque_ptr(value + img);
-    typename ACC::elem *gimg = opaque_ptr(gv_acc + img);
+    const T *vimg = value + img;
+    typename ACC::elem *gimg = gv_acc + img;
     ACC accp;
     if constexpr (sizeof(typename ACC::elem) == 8) accp.scale = __ldg(det_scale);
     accp.template prepare<T, E>(grad_out + row * D, sub, LPT);

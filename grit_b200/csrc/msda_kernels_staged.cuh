@@ -14,8 +14,12 @@
 //     work on a few images whose maps stay L2-resident): the hardware block scheduler hands them out as SMs free up.
 //     The first version of this kernel (round 1) was persistent with a static slice of the rows per SM; B200's SMs do
 //     not run at one speed (two dies, per-GPU SM -> L2 distance map), so static slices left a tail that made the kernel
-//     slower than the row kernel on some boxes (1.53 vs 1.47 ms) and faster on others (1.34 ms).  Staging costs 169 KB
-//     of L2 reads per item against ~4 500 rows x 8 KB of taps (< 1 %).
+//     slower than the row kernel on some boxes (1.53 vs 1.47 ms) and faster on others (1.34 ms); items of ~1024 rows keep
+//     the scheduler's granularity fine (5 chunks per (image, head) lost a fifth to wave quantisation, 1.54 ms) while
+//     staging costs 169 KB of L2 reads per 8 MB of taps.
+//   * it is the default only where at least three of four levels fit on chip (a 384x640-class pyramid: 0.60 vs 0.62 ms
+//     for the row kernel); with two levels staged (800x1333) the row kernel, at 1.31 ms after its addressing was cut to
+//     one IMAD.WIDE per tap, beats the staged kernel's 1.34 ms (profiles/r02_staged_ab.txt).
 #pragma once
 
 #include "msda_common.cuh"
@@ -95,7 +99,6 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
     const int MD = M * D;
     const int rp = lane % LP, rl = rp / P;
     const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
-
     // item = (image, chunk, head), head fastest: item = (b * chunks + c) * M + m.  The grid normally has one CTA per
     // item (dynamic scheduling by the hardware); a smaller grid walks the items round-robin (A/B knob "staged_persistent").
     const unsigned n_items = (unsigned)N * (unsigned)chunks * (unsigned)M;
@@ -158,8 +161,8 @@ msda_fwd_v3(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
                     const float a = __shfl_sync(0xffffffffu, mine.a, pt);
                     const float lh = __shfl_sync(0xffffffffu, mine.lh, pt);
                     const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
-                    const int W = plan.W[l];
-                    const int sb = plan.sbase[l];
+                    const int W = plan.W[l];   // (keeping these two in registers across rows was measured slower:
+                    const int sb = plan.sbase[l];  //  the kernel sits at its 64-register budget)
                     const int pix = pm >> 4;
                     float v0[E], v1[E], v2[E], v3[E];
                     if (sb != kNotStaged) {  // taps from the staged plane: LDS.128, 32-bit offsets
