@@ -628,6 +628,44 @@ def main():
                             "fwd_bwd_queries_per_s": c2["N"] * Lq2 / ((f_ms + b_ms) * 1e-3),
                             "fwd_hbm_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_hbm_frac": bb / (b_ms * 1e-3) / 1e9 / peak}
             del x
+        # GRIT's real operating point (no AMP: fp32, 150 queries, C=512 / D=64; det_module.py:285,335-336) at batch 4 / 16 /
+        # 64, with the HBM-roofline fraction of each direction and the reference's own CUDA kernels beside them
+        ref_so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttentionRef.so")
+        refmod = None
+        if os.path.exists(ref_so):
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttentionRef", ref_so)
+                refmod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(refmod)
+            except Exception:
+                refmod = None
+        for name in ("grit_decoder_384x640_f32", "grit_decoder_800x1333_f32"):
+            for nb in (4, 16, 64):
+                c2 = dict(WORKLOADS[name], N=nb)
+                x = make_layer_inputs(torch, c2, device, 5, "uniform")
+                sh = torch.tensor(c2["shapes"], dtype=torch.int64, device=device)
+                ls = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+                f_ms, b_ms = time_pair(x, lambda s_: _lib.forward(s_["value"], sh, ls, s_["loc"], s_["attn"]),
+                                       lambda s_: _lib.backward(s_["value"], sh, ls, s_["loc"], s_["attn"], s_["gout"]),
+                                       iters=20)
+                S2 = sum(h * w for h, w in c2["shapes"])
+                fb, bb = algorithmic_bytes(nb, S2, c2["Lq"], c2["M"], c2["D"], len(c2["shapes"]), c2["P"], 4)
+                entry = {"fwd_us": f_ms * 1e3, "bwd_us_incl_alloc_zero": b_ms * 1e3,
+                         "fwd_hbm_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_hbm_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
+                         "fwd_bwd_queries_per_s": nb * c2["Lq"] / ((f_ms + b_ms) * 1e-3)}
+                if refmod is not None:
+                    try:
+                        rf, rb = time_pair(
+                            x, lambda s_: refmod.ms_deform_attn_forward(s_["value"], sh, ls, s_["loc"], s_["attn"], 64),
+                            lambda s_: refmod.ms_deform_attn_backward(s_["value"], sh, ls, s_["loc"], s_["attn"],
+                                                                      s_["gout"], 64), iters=20)
+                        entry.update(ref_cuda_fwd_us=rf * 1e3, ref_cuda_bwd_us=rb * 1e3,
+                                     speedup_vs_ref_cuda=(rf + rb) / (f_ms + b_ms))
+                    except Exception as exc:
+                        entry["ref_cuda"] = repr(exc)[:120]
+                extras[f"{name}_N{nb}"] = entry
+                del x
         # the module around the op (4 Linears + pre-op arithmetic + op), reference-shaped path vs fused kernels (8f-1)
         if dt == torch.float32:
             try:
@@ -667,13 +705,8 @@ def main():
                 del mod, mq, ms_, mr, mg, mm
             except Exception as exc:
                 extras["module_fwd_bwd_ms"] = {"unavailable": repr(exc)[:200]}
-        ref_so = os.path.join(ROOT, "baseline", "_ref", "MultiScaleDeformableAttentionRef.so")
-        if os.path.exists(ref_so) and dt == torch.float32:
+        if refmod is not None and dt == torch.float32:
             try:
-                import importlib.util
-                spec = importlib.util.spec_from_file_location("MultiScaleDeformableAttentionRef", ref_so)
-                refmod = importlib.util.module_from_spec(spec)
-                spec.loader.exec_module(refmod)
                 s0 = sets[0]
                 f_ms, b_ms = time_pair(
                     s0, lambda s: refmod.ms_deform_attn_forward(s["value"], shapes, lsi, s["loc"], s["attn"], 64),
