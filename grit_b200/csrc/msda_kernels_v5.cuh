@@ -179,6 +179,8 @@ __device__ __forceinline__ void fwd_row_body_hoisted(const Resolved &mine, const
     }
 }
 
+// (40 registers, 12 CTAs per SM.  A 32-register build -- __launch_bounds__(128, 16), 64 resident warps -- spills and
+//  measured 1.38 vs 1.31 ms; naming a minimum of ONE CTA per SM makes ptxas spend 92 registers and costs 35 %.)
 template <typename T, int D, int L, int P, int WARPS, bool HOIST = false>
 __global__ void __launch_bounds__(WARPS * 32)
 msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
@@ -366,41 +368,47 @@ msda_bwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
 // ---- deterministic mode helpers ---------------------------------------------------------------------------------------
 // workspace tail: [0] = max|attn| bits, [1] = max|grad_out| bits (uint, monotone for non-negative floats),
 //                 [2] = scale 2^k (float), [3] = 2^-k (float)
+// The maxima are taken on the BIT PATTERNS of |x| (monotone for non-negative floats, and Inf / NaN compare above every
+// finite value), so a non-finite input is not silently dropped the way fmaxf would drop a NaN.
 template <typename T>
 __global__ void msda_det_absmax(const float *__restrict__ attn, int64_t n_attn, const T *__restrict__ gout,
                                 int64_t n_gout, unsigned *__restrict__ tail)
 {
-    float ma = 0.f, mg = 0.f;
+    unsigned ma = 0u, mg = 0u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_attn; i += stride) ma = fmaxf(ma, fabsf(attn[i]));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_attn; i += stride)
+        ma = max(ma, __float_as_uint(fabsf(attn[i])));
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_gout; i += stride)
-        mg = fmaxf(mg, fabsf(to_c<float, T>(gout[i])));
+        mg = max(mg, __float_as_uint(fabsf(to_c<float, T>(gout[i]))));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, off));
-        mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+        ma = max(ma, __shfl_xor_sync(0xffffffffu, ma, off));
+        mg = max(mg, __shfl_xor_sync(0xffffffffu, mg, off));
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicMax(tail + 0, __float_as_uint(ma));
-        atomicMax(tail + 1, __float_as_uint(mg));
+        atomicMax(tail + 0, ma);
+        atomicMax(tail + 1, mg);
     }
 }
 
 // One thread: k = 61 - ceil(log2(worst-case addends)) - exponent(max|attn| * max|grad_out|), so that the int64 sums
-// cannot overflow whatever the sampling pattern is.
+// cannot overflow whatever the sampling pattern is.  Non-finite inputs (an overflowed loss scale, a NaN upstream) cannot
+// be represented in fixed point: the inverse scale becomes NaN, so the fold writes NaN into all of grad_value -- loud,
+// like the float path, instead of a clean-looking gradient.
 __global__ void msda_det_scale(unsigned *tail, double worst_addends, float attn_bound)
 {
     // attn_bound > 0: the caller knows max|attn| a priori (softmax output <= 1 in the fused path)
+    const bool finite = (attn_bound > 0.f || tail[0] <= 0x7f7fffffu) && tail[1] <= 0x7f7fffffu;
     const float ma = attn_bound > 0.f ? attn_bound : __uint_as_float(tail[0]);
     const float mg = __uint_as_float(tail[1]);
     int e_prod = 0, e_n = 0;
     frexp((double)ma * (double)mg, &e_prod);  // product < 2^e_prod
     frexp(worst_addends, &e_n);                // addends < 2^e_n
     int k = 61 - e_n - e_prod;
-    if (!(ma > 0.f) || !(mg > 0.f)) k = 0;     // all-zero (or NaN) inputs: any scale works
+    if (!finite || !(ma > 0.f) || !(mg > 0.f)) k = 0;  // all-zero inputs: any scale works
     k = max(-100, min(100, k));
     reinterpret_cast<float *>(tail)[2] = ldexpf(1.f, k);
-    reinterpret_cast<float *>(tail)[3] = ldexpf(1.f, -k);
+    reinterpret_cast<float *>(tail)[3] = finite ? ldexpf(1.f, -k) : __uint_as_float(0x7fc00000u);
 }
 
 template <typename T>

@@ -11,6 +11,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="detr_encoder_800x1333")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--configs", default="all", help="all | row (row-kernel knobs only)")
 args = ap.parse_args()
 lib = _lib.load()
 dev = torch.device("cuda", 0)
@@ -42,6 +43,9 @@ configs = [("row_v5", {"variant": 5})] + \
     [(f"staged_persistent_rows{r}", {"variant": 3, "staged_rows": r, "staged_persistent": 1}) for r in (512, 1024, 4445)] + \
     [("staged_768thr_rows1024", {"variant": 3, "staged_rows": 1024, "v3_threads": 768}),
      ("staged_512thr_rows1024", {"variant": 3, "staged_rows": 1024, "v3_threads": 512})]
+if args.configs == "row":
+    configs = [("row_v5", {"variant": 5}), ("row_v5_w8", {"variant": 5, "warps": 8}),
+               ("row_v5_hoist", {"variant": 5, "hoist": 1})]
 res = {}
 for rep in range(args.reps):
     for name, knobs in configs:

@@ -907,3 +907,66 @@ def test_reference_test_py_runs_unchanged(lib, tmp_path):
     assert len(lines) == 6, proc.stdout  # 2 forward checks + gradcheck for D in {30, 32, 64, 71}
     for ln in lines:
         assert ln.startswith("* True"), ln
+
+
+def test_deterministic_backward_does_not_hide_non_finite_gradients(lib):
+    """a NaN / Inf in grad_output cannot be represented in the deterministic mode's fixed point; it must come
+    out as NaN in grad_value (loud), not as a clean-looking gradient."""
+    case = helpers.make_inputs(1, 40, 8, 32, SMALL_PYR, 4, seed=8, dtype=np.float32)
+    for bad in (np.nan, np.inf):
+        c = dict(case, grad_out=case["grad_out"].copy())
+        c["grad_out"][0, 3, 5] = bad
+        got = run_kernels(lib, c, torch.float32, flags=lib.FLAG_DETERMINISTIC)
+        assert "deterministic" in got["bwd_kernel"]
+        assert torch.isnan(got["grad_value"]).any()
+    clean = run_kernels(lib, case, torch.float32, flags=lib.FLAG_DETERMINISTIC)
+    assert torch.isfinite(clean["grad_value"]).all()
+
+
+def test_host_submit_wait_pipelines_several_calls(lib, oracle):
+    """msda_host_submit x3 (different inputs, different output buffers, one of them with another pyramid so the level
+    metadata is re-uploaded mid-pipeline) + one msda_host_wait == three synchronous calls == the oracle."""
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().contiguous().pin_memory()
+    other_pyr = [(10, 24), (6, 10), (3, 5), (2, 3)]  # same S as SMALL_PYR (12*20 = 10*24), different level shapes
+    problems = []
+    for seed, pyr in ((11, SMALL_PYR), (12, SMALL_PYR), (13, other_pyr)):
+        case = helpers.rounded_case(helpers.make_inputs(5, 33, 8, 32, pyr, 4, seed=seed), torch.float32)
+        t = {k: pin(case[k]) for k in ("value", "loc", "attn", "grad_out")}
+        t["shapes"], t["lsi"] = torch.from_numpy(case["shapes"]), torch.from_numpy(case["level_start"])
+        t["out"] = torch.empty(5, 33, 256).pin_memory()
+        t["gv"], t["gl"], t["ga"] = (torch.empty_like(t[k]).pin_memory() for k in ("value", "loc", "attn"))
+        problems.append((case, t))
+    dims = lib.MsdaDims(5, problems[0][1]["value"].shape[1], 8, 32, 4, 33, 4)
+    sess = lib.HostSession(dims, torch.float32, device=0, images_per_chunk=2)
+    for _, t in problems:
+        sess.submit(t["value"], t["shapes"], t["lsi"], t["loc"], t["attn"], t["grad_out"], t["out"], t["gv"], t["gl"], t["ga"])
+    sess.wait()
+    for case, t in problems:
+        ref = oracle_results(oracle, case)
+        assert max_norm_err(t["out"].numpy(), ref["out"]) < 1e-5
+        assert max_norm_err(t["gv"].numpy(), ref["grad_value"]) < 1e-4
+        assert max_norm_err(t["ga"].numpy(), ref["grad_attn"]) < 1e-4
+    sess.close()
+
+
+def test_backward_strategy_selection_for_the_baseline_configs(lib):
+    """msda_backward_strategy (include/msda.h): the automatic choice for BASELINE.json's shapes -- 1 = row reds, 3 = owned."""
+    import ctypes
+    raw = lib.load()
+    S_big, S_small = 22223, 5100
+    pick = lambda n, s, d, lq, dt, flags=0: raw.msda_backward_strategy(
+        ctypes.byref(lib.MsdaDims(n, s, 8, d, 4, lq, 4)), lib._DTYPE_CODE[dt], flags)
+    assert pick(16, S_big, 32, S_big, torch.float32) == 1     # config 3: dense encoder -> row kernel
+    assert pick(32, S_small, 32, S_small, torch.float32) == 1  # config 2
+    assert pick(32, S_big, 32, S_big, torch.bfloat16) == 1     # config 5, encoder half: dense -> row kernel
+    assert pick(32, S_big, 64, 150, torch.bfloat16) == 3       # config 4 / 5, decoder half in bf16 -> owned
+    assert pick(64, S_small, 64, 150, torch.bfloat16) == 3
+    assert pick(64, S_small, 64, 150, torch.float32) == 1      # GRIT's fp32 decoder: both strategies tie, row kept
+    assert pick(2, S_small, 64, 150, torch.bfloat16) == 1      # too small to be bandwidth-bound
+    assert pick(32, S_big, 64, 150, torch.bfloat16, lib.FLAG_DETERMINISTIC) == 1
+    assert pick(32, S_big, 64, 150, torch.float64) == 1
+    prev = lib.set_tuning("bwd_mode", 2)
+    try:
+        assert pick(16, S_big, 32, S_big, torch.float32) == 2
+    finally:
+        lib.set_tuning("bwd_mode", prev)
