@@ -65,9 +65,12 @@ def main():
         P_ = _lib._ptr
         fb, bb = bench.algorithmic_bytes(N, S, Lq, M, D, L, P, ev)
 
+        fws_bytes = lib.msda_forward_workspace_bytes(ctypes.byref(dims), code, 0)
+        fws = torch.empty(max(fws_bytes, 16), dtype=torch.uint8, device=dev)
+
         def fwd():
-            rc = lib.msda_forward(P_(x["value"]), P_(shapes), P_(lsi), P_(x["loc"]), P_(x["attn"]), P_(out),
-                                  ctypes.byref(dims), code, 0, st)
+            rc = lib.msda_forward_ws(P_(x["value"]), P_(shapes), P_(lsi), P_(x["loc"]), P_(x["attn"]), P_(out),
+                                     ctypes.byref(dims), code, 0, P_(fws), fws_bytes, st)
             assert rc == 0, lib.msda_last_error()
 
         def bwd():
@@ -88,7 +91,7 @@ def main():
             return a.elapsed_time(b) / args.iters
 
         res = {"N": N, "Lq": Lq, "S": S, "D": D, "dtype": cfg["dtype"], "fwd_alg_MB": fb / 1e6, "bwd_alg_MB": bb / 1e6}
-        for variant in (5, 3):
+        for variant in (0, 5, 3):
             prev = _lib.set_tuning("variant", variant)
             try:
                 ms = timeit(fwd)
