@@ -384,12 +384,9 @@ def main():
                         "grad_loc/grad_attn all-gathered and compared; bucket all-reduce of a rank-dependent pattern "
                         "checked against its closed form"}
 
-    fws_bytes = lib.msda_forward_workspace_bytes(ctypes.byref(dims), code, 0)  # bf16 D=32: pair-packed copy of value
-    fws = torch.empty(max(fws_bytes, 16), dtype=torch.uint8, device=device)
-
-    def fwd(s):  # the packing pass, when used, is inside this call and so inside every timed bracket
-        rc = lib.msda_forward_ws(P_(s["value"]), P_(shapes), P_(lsi), P_(s["loc"]), P_(s["attn"]), P_(out),
-                                 ctypes.byref(dims), code, 0, P_(fws), fws_bytes, ctypes.c_void_p(stream))
+    def fwd(s):
+        rc = lib.msda_forward(P_(s["value"]), P_(shapes), P_(lsi), P_(s["loc"]), P_(s["attn"]), P_(out),
+                              ctypes.byref(dims), code, 0, ctypes.c_void_p(stream))
         if rc:
             raise RuntimeError(lib.msda_last_error().decode())
 

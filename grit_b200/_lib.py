@@ -79,11 +79,6 @@ def load():
         lib.msda_set_tuning.argtypes = [ctypes.c_char_p, ctypes.c_int]
         lib.msda_forward.restype = ctypes.c_int
         lib.msda_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint, vp]
-        lib.msda_forward_workspace_bytes.restype = ctypes.c_size_t
-        lib.msda_forward_workspace_bytes.argtypes = [dimsp, ctypes.c_int, ctypes.c_uint]
-        lib.msda_forward_ws.restype = ctypes.c_int
-        lib.msda_forward_ws.argtypes = [vp, i64p, i64p, vp, vp, vp, dimsp, ctypes.c_int, ctypes.c_uint, vp,
-                                        ctypes.c_size_t, vp]
         lib.msda_backward_strategy.restype = ctypes.c_int
         lib.msda_backward_strategy.argtypes = [dimsp, ctypes.c_int, ctypes.c_uint]
         lib.msda_backward_workspace_bytes.restype = ctypes.c_size_t
@@ -232,14 +227,11 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     dims = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
-    code = _DTYPE_CODE[value.dtype]
-    ws_bytes = lib.msda_forward_workspace_bytes(ctypes.byref(dims), code, flags)  # bf16 D=32: pair-packed copy of value
-    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=value.device) if ws_bytes else None
     with torch.cuda.device(value.device), _nvtx_range("msda_forward"):
         stream = torch.cuda.current_stream().cuda_stream
-        rc = lib.msda_forward_ws(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
-                                 _ptr(attn_weight), _ptr(out), ctypes.byref(dims), code, flags,
-                                 _ptr(workspace) if workspace is not None else None, ws_bytes, ctypes.c_void_p(stream))
+        rc = lib.msda_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
+                              _ptr(attn_weight), _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], flags,
+                              ctypes.c_void_p(stream))
     if rc:
         _raise(lib, rc, "msda_forward")
     if not flags & FLAG_FORCE_GENERIC:

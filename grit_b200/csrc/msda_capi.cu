@@ -13,7 +13,6 @@
 
 #include "msda_kernels_fused.cuh"
 #include "msda_kernels_layer.cuh"
-#include "msda_kernels_pairs.cuh"
 #include "msda_kernels_staged.cuh"
 
 #include <atomic>
@@ -79,7 +78,6 @@ std::atomic<int> g_variant{0};        // forward: 0 = auto (default) | 5 = lean 
 std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 1024
 std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
-std::atomic<int> g_pairs{1};          // bf16 D=32 forward through the pair-packed copy of value when a workspace is given
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
 std::atomic<int> g_staged_rows{1024};     // staged forward: query rows per work item (CTA)
 std::atomic<int> g_staged_persistent{0};  // staged forward A/B: 1 = one CTA per SM walking the items round-robin
@@ -513,7 +511,6 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "v3_threads")) knob = &g_v3_threads;
     if (key && !strcmp(key, "hoist")) knob = &g_hoist;
     if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
-    if (key && !strcmp(key, "pairs")) knob = &g_pairs;
     if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
     if (key && !strcmp(key, "staged_min_rows")) knob = &g_staged_min_rows;
     if (key && !strcmp(key, "staged_rows")) knob = &g_staged_rows;
@@ -590,53 +587,6 @@ int msda_backward_strategy(const msda_dims *dims, int dtype, unsigned flags)
 {
     if (check_dims(dims, dtype) != MSDA_OK) return 0;
     return choose_bwd_mode(dims, dtype, flags);
-}
-
-// ---- bf16 forward through the pair-packed copy of value (msda_kernels_pairs.cuh) -----------------------------------------
-static bool pairs_applicable(const msda_dims *d, int dtype, unsigned flags)
-{
-    if (dtype != MSDA_BF16 || d->channels != 32 || d->num_levels != 4 || d->num_point != 4) return false;
-    if (!g_pairs.load() || g_variant.load() != 0 || !vec_eligible(d, dtype, flags)) return false;
-    if (d->batch * d->num_query * d->num_heads == 0 || d->spatial_size == 0) return false;
-    // worth the packing pass (3 V bytes of traffic) only when every (pixel, head) line is gathered many times
-    const int64_t taps = d->num_query * d->num_levels * d->num_point * 4;
-    return taps >= 8 * d->spatial_size && msda::pairs_padded_pixels(d->spatial_size) * 64 < ((int64_t)1 << 31);
-}
-
-size_t msda_forward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags)
-{
-    if (check_dims(dims, dtype) != MSDA_OK || !pairs_applicable(dims, dtype, flags)) return 0;
-    return (size_t)(dims->batch * dims->num_heads * 2 * msda::pairs_padded_pixels(dims->spatial_size) * 32) * 2;
-}
-
-int msda_forward_ws(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                    const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims, int dtype,
-                    unsigned flags, void *workspace, size_t workspace_bytes, void *cuda_stream)
-{
-    tl_error[0] = 0;
-    if (int rc = check_dims(dims, dtype)) return rc;
-    const size_t need = msda_forward_workspace_bytes(dims, dtype, flags);
-    if (need == 0 || !workspace || workspace_bytes < need || !aligned16(workspace) || !aligned16(value) ||
-        !aligned16(output) || (reinterpret_cast<uintptr_t>(sampling_loc) & 7u))
-        return msda_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, dims, dtype, flags,
-                            cuda_stream);
-    if (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight || !output)
-        return fail(MSDA_ERR_INVALID_ARGUMENT, "null tensor pointer");
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int S = (int)dims->spatial_size, M = (int)dims->num_heads;
-    const int64_t Sp = msda::pairs_padded_pixels(S);
-    auto *packed = (__nv_bfloat16 *)workspace;
-    msda::msda_pack_pairs<<<dim3((unsigned)((S + 7) / 8), (unsigned)dims->batch), 256, 0, st>>>(
-        (const __nv_bfloat16 *)value, packed, S, M, Sp);
-    msda::msda_pack_pairs_pad<<<(unsigned)(dims->batch * M), 32, 0, st>>>(packed, S, Sp);
-    constexpr int W = 4;
-    const unsigned rpi = (unsigned)(dims->num_query * dims->num_heads);
-    msda::msda_fwd_pairs<4, 4, W><<<dim3((rpi + W - 1) / W, (unsigned)dims->batch), W * 32, 0, st>>>(
-        packed, spatial_shapes, level_start_index, (const float *)sampling_loc, (const float *)attn_weight,
-        (__nv_bfloat16 *)output, S, M, rpi, Sp);
-    tl_launches += 3;
-    snprintf(tl_kernel, sizeof(tl_kernel), "pack_pairs+fwd_pairs<bf16,D32,L4,P4,w%d>", W);
-    return check_cuda(cudaPeekAtLastError(), "msda_forward_ws launch");
 }
 
 size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags)

@@ -98,7 +98,6 @@ int64_t msda_launch_count(int reset);
  *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
  *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
- *   "pairs"          1 (default) | 0: msda_forward_ws may use the pair-packed bf16 path
  *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
  *                    2 row kernel + on-SM aggregation of the coarse levels (msda_bwd_binned) |
  *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems)
@@ -115,17 +114,6 @@ int msda_set_tuning(const char *key, int value);
 int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                  const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims,
                  int dtype, unsigned flags, void *cuda_stream);
-
-/* bf16, D = 32: the gather is bound by 128-byte requests, and a 64-byte bf16 tap costs a request of its own in the (N,S,M,D)
- * layout.  With a scratch buffer the forward first re-packs value head-major, twice (second copy shifted by one pixel), so the
- * two horizontal taps of every sample are ONE aligned 128-byte line, and gathers from that: half the requests.
- * msda_forward_workspace_bytes says how much scratch that takes (0 = not applicable: other dtypes / widths, or problems
- * with too few taps per pixel to amortise the packing pass); msda_forward_ws is msda_forward with the scratch (16-byte
- * aligned; anything smaller than requested, or NULL, falls back to msda_forward). */
-size_t msda_forward_workspace_bytes(const msda_dims *dims, int dtype, unsigned flags);
-int msda_forward_ws(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
-                    const void *sampling_loc, const void *attn_weight, void *output, const msda_dims *dims, int dtype,
-                    unsigned flags, void *workspace, size_t workspace_bytes, void *cuda_stream);
 
 /* Bytes of device scratch msda_backward needs for this problem: 0 for f32/f64; N*S*M*D*4 for bf16 (fp32 image of
  * grad_value; 0 with MSDA_FLAG_ALIGNED16 when the owned backward applies); N*S*M*D*8 + 16 with

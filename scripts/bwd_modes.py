@@ -65,12 +65,9 @@ def main():
         P_ = _lib._ptr
         fb, bb = bench.algorithmic_bytes(N, S, Lq, M, D, L, P, ev)
 
-        fws_bytes = lib.msda_forward_workspace_bytes(ctypes.byref(dims), code, 0)
-        fws = torch.empty(max(fws_bytes, 16), dtype=torch.uint8, device=dev)
-
         def fwd():
-            rc = lib.msda_forward_ws(P_(x["value"]), P_(shapes), P_(lsi), P_(x["loc"]), P_(x["attn"]), P_(out),
-                                     ctypes.byref(dims), code, 0, P_(fws), fws_bytes, st)
+            rc = lib.msda_forward(P_(x["value"]), P_(shapes), P_(lsi), P_(x["loc"]), P_(x["attn"]), P_(out),
+                                  ctypes.byref(dims), code, 0, st)
             assert rc == 0, lib.msda_last_error()
 
         def bwd():

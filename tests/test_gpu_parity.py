@@ -970,30 +970,3 @@ def test_backward_strategy_selection_for_the_baseline_configs(lib):
         assert pick(16, S_big, 32, S_big, torch.float32) == 2
     finally:
         lib.set_tuning("bwd_mode", prev)
-
-
-@pytest.mark.parametrize("shapes,Lq,N", [
-    ([(40, 60), (20, 30), (10, 15), (5, 8)], 501, 2),      # even S
-    ([(33, 35), (1, 9), (7, 1), (2, 2)], 257, 3),          # odd S, a 1-pixel-high and a 1-pixel-wide level (every pair wraps)
-    ([(9, 7), (5, 5), (3, 3), (1, 1)], 97, 2),             # odd widths everywhere: pairs alternate between the two copies
-])
-def test_pair_packed_bf16_forward_vs_oracle(lib, oracle, shapes, Lq, N):
-    """msda_forward_ws: bf16, D=32 through the pair-packed copy of value (two horizontal taps = one aligned 128-byte line)
-    == the fp64 oracle and == the row kernel bit for bit is NOT expected (different summation order), so both are held to
-    the bf16 tolerance; out-of-range samples on every side."""
-    dtype = torch.bfloat16
-    case = helpers.rounded_case(helpers.make_inputs(N, Lq, 8, 32, shapes, 4, seed=Lq, lo=-0.3, hi=1.3), dtype)
-    t = helpers.to_cuda(case, dtype)
-    out = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"])
-    assert lib.last_kernel().startswith("pack_pairs+fwd_pairs"), lib.last_kernel()
-    prev = lib.set_tuning("pairs", 0)
-    try:
-        out_row = lib.forward(t["value"], t["shapes"], t["level_start"], t["loc"], t["attn"])
-        assert lib.last_kernel().startswith("fwd_"), lib.last_kernel()
-    finally:
-        lib.set_tuning("pairs", prev)
-    ref = oracle.forward(case["value"], case["shapes"], case["level_start"], case["loc"], case["attn"])
-    assert max_norm_err(out.double().cpu().numpy(), ref) <= TOL[dtype][0]
-    assert max_norm_err(out_row.double().cpu().numpy(), ref) <= TOL[dtype][0]
-    # NaN in an unused padding / out-of-range position must not leak: poison value's last pixel rows and a masked sample
-    assert torch.isfinite(out).all()
