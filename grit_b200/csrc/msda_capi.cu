@@ -14,6 +14,7 @@
 #include "msda_kernels_fused.cuh"
 #include "msda_kernels_layer.cuh"
 #include "msda_kernels_staged.cuh"
+#include "msda_kernels_planes.cuh"
 
 #include <atomic>
 #include <type_traits>
@@ -79,6 +80,11 @@ std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 10
 std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
+                                      //           | 4 planes (coarse levels in shared-memory int32 fixed point)
+std::atomic<int> g_planes_rows{1024};     // planes backward: query rows per work item (CTA)
+std::atomic<int> g_planes_threads{768};  // planes backward CTA size: 512, 768 or 1024
+std::atomic<int> g_planes_auto{1};        // auto: 0 = never choose the planes backward by default
+std::atomic<int> g_planes_budget{-1};     // planes backward A/B: cap on the plane bytes (-1 = all the shared memory)
 std::atomic<int> g_staged_rows{1024};     // staged forward: query rows per work item (CTA)
 std::atomic<int> g_staged_persistent{0};  // staged forward A/B: 1 = one CTA per SM walking the items round-robin
 std::atomic<int> g_staged_min_rows{200};  // auto: staged forward (D=32) when num_heads*num_query / #SMs >= this
@@ -329,7 +335,7 @@ int launch_fwd_staged(const msda_dims *d, const void *value, const int64_t *shap
 }
 
 // ---- grad_value by on-SM aggregation (msda_kernels_binned.cuh) -------------------------------------------
-enum { BWD_ROW = 1, BWD_BINNED = 2, BWD_OWNED = 3 };
+enum { BWD_ROW = 1, BWD_BINNED = 2, BWD_OWNED = 3, BWD_PLANES = 4 };
 
 bool flagship_spec(const msda_dims *d)
 {
@@ -404,6 +410,7 @@ int choose_bwd_mode(const msda_dims *d, int dtype, unsigned flags)
     const bool can_own = owned_plan(d, &op);
     if (forced == BWD_BINNED) return can_bin ? BWD_BINNED : BWD_ROW;
     if (forced == BWD_OWNED) return can_own ? BWD_OWNED : BWD_ROW;
+    if (forced == BWD_PLANES) return BWD_PLANES;
     // owned pays where the row path's zero-fill / workspace / fold traffic dominates: sparse problems in bf16 (fp32
     // image of grad_value zero-filled, accumulated, read back, folded) that are large enough to be bandwidth- rather
     // than launch-bound.  For fp32 both strategies write grad_value once and measure the same.
@@ -414,6 +421,16 @@ int choose_bwd_mode(const msda_dims *d, int dtype, unsigned flags)
         return BWD_OWNED;
     const int bin_min = g_bin_min_rows.load();
     if (can_bin && bin_min > 0 && d->num_levels >= 2 && d->num_query >= bin_min) return BWD_BINNED;
+    // planes (coarse levels accumulated in shared memory as int32 fixed point) where it measured faster than the row
+    // kernel (profiles/r02_planes_*.json): dense D=32 problems with enough rows to fill the machine, when three of the
+    // four gradient planes fit in shared memory (384x640 class, -10 %; same 4:1-pyramid assumption as the staged
+    // forward: the host does not read spatial_shapes) or in bf16 (800x1333: -7 %).  At 800x1333 in fp32 with uniform
+    // locations both run at 3.5 ms, so the row kernel (plain fp32 sums) stays.
+    if (g_planes_auto.load() && d->channels == 32 && taps > (int64_t)g_owned_max_taps.load() * d->spatial_size &&
+        d->num_heads * d->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms) {
+        const int64_t coarse_plane_bytes = d->spatial_size / 4 * d->channels * 4;
+        if (dtype == MSDA_BF16 || coarse_plane_bytes <= device_info().max_smem_optin - 8192) return BWD_PLANES;
+    }
     return BWD_ROW;
 }
 
@@ -455,6 +472,49 @@ int launch_bwd_owned(const msda_dims *d, const OwnedPlan &op, const int64_t *sha
     MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
 #undef X
     return fail(MSDA_ERR_UNSUPPORTED, "no owned backward for this shape");
+}
+
+// ---- coarse levels in shared-memory fixed-point planes (msda_kernels_planes.cuh) ------------------------------------
+template <typename T, int DD, int LL, int PP, int TH>
+int bwd_planes_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                      const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    using CH = typename BwdChunk<T>::type;
+    auto kernel = msda::msda_bwd_planes<T, CH, DD, LL, PP, TH>;
+    const int smem = (device_info().max_smem_optin - 2048 - (TH / 32) * DD * 4) & ~15;  // minus the static shared memory
+    if (smem <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
+    if (int rc = optin_smem(kernel, smem)) return rc;
+    int rows_per_item = g_planes_rows.load();
+    if (rows_per_item < 64) rows_per_item = 64;
+    int64_t chunks = (d->num_query + rows_per_item - 1) / rows_per_item;
+    if (chunks < 1) chunks = 1;
+    const int64_t items = d->batch * chunks * d->num_heads;
+    if (items > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
+    const int cap = g_planes_budget.load();
+    kernel<<<(unsigned)items, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
+                                              (const T *)gout, gv_acc, (float *)gloc, (float *)gattn, (int)d->batch,
+                                              (int)d->spatial_size, (int)d->num_heads, (int)d->num_query,
+                                              (cap >= 0 && cap < smem ? cap : smem) / 4, (int)chunks);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_planes<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
+    return MSDA_OK;
+}
+
+// returns -1 when no specialisation matches, else a status code
+template <typename T>
+int launch_bwd_planes(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
+                      const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
+{
+    const int th = g_planes_threads.load();
+#define X(DD, LL, PP)                                                                                                  \
+    if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                                         \
+        return th >= 1024                                                                                              \
+                   ? bwd_planes_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st) \
+               : th >= 768                                                                                             \
+                   ? bwd_planes_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st)  \
+                   : bwd_planes_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st);
+    MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
+#undef X
+    return -1;
 }
 
 // ---- generic kernels -----------------------------------------------------------------------------------------------
@@ -516,6 +576,10 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "staged_rows")) knob = &g_staged_rows;
     if (key && !strcmp(key, "staged_persistent")) knob = &g_staged_persistent;
     if (key && !strcmp(key, "owned_max_taps")) knob = &g_owned_max_taps;
+    if (key && !strcmp(key, "planes_rows")) knob = &g_planes_rows;
+    if (key && !strcmp(key, "planes_threads")) knob = &g_planes_threads;
+    if (key && !strcmp(key, "planes_budget")) knob = &g_planes_budget;
+    if (key && !strcmp(key, "planes_auto")) knob = &g_planes_auto;
     if (!knob) return -1;
     return knob->exchange(value);
 }
@@ -784,7 +848,18 @@ int msda_backward(const void *value, const int64_t *spatial_shapes, const int64_
     const float *det_scale = plan.det_scale;
 
     bool done = false;
-    if (vec_ok && aligned16(gv_acc)) {
+    if (mode == BWD_PLANES && vec_ok && aligned16(gv_acc) && !det_scale) {
+        const int rc = dtype == MSDA_F32
+                           ? launch_bwd_planes<float>(dims, value, spatial_shapes, level_start_index, sampling_loc,
+                                                      attn_weight, grad_output, (float *)gv_acc, grad_sampling_loc,
+                                                      grad_attn_weight, st)
+                           : launch_bwd_planes<__nv_bfloat16>(dims, value, spatial_shapes, level_start_index,
+                                                              sampling_loc, attn_weight, grad_output, (float *)gv_acc,
+                                                              grad_sampling_loc, grad_attn_weight, st);
+        if (rc > 0) return rc;
+        done = rc == 0;
+    }
+    if (!done && vec_ok && aligned16(gv_acc)) {
         const int skip = mode == BWD_BINNED ? bp.acc_budget : 0;
         done = dtype == MSDA_F32
                    ? launch_bwd_v5<float>(dims, value, spatial_shapes, level_start_index, sampling_loc, attn_weight,

@@ -96,6 +96,12 @@ struct ChunkBf16x4 {
         r[0] = __uint_as_float(v.x << 16), r[1] = __uint_as_float(v.x & 0xffff0000u);
         r[2] = __uint_as_float(v.y << 16), r[3] = __uint_as_float(v.y & 0xffff0000u);
     }
+    __device__ __forceinline__ static void load_shared(const __nv_bfloat16 *p, float (&r)[4])
+    {
+        const uint2 v = *reinterpret_cast<const uint2 *>(p);
+        r[0] = __uint_as_float(v.x << 16), r[1] = __uint_as_float(v.x & 0xffff0000u);
+        r[2] = __uint_as_float(v.y << 16), r[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
 };
 
 // fire-and-forget vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+)

@@ -106,6 +106,9 @@ __device__ __forceinline__ void load_taps(const T *vimg, int o0, int o1, int o2,
     }
 }
 
+// (Choosing the fast path per ITERATION by a warp vote inside the general body -- 94 / 88 / 77 / 60 % of the iterations
+//  of levels 0..3 qualify with uniform locations, against 38 % of whole rows -- was measured slower: 48 instead of 40
+//  registers, 10 instead of 12 CTAs per SM, 1.43 vs 1.31 ms.)
 template <typename T, int D, int L, int P, bool ALL>
 __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg, int MD, const int (&sW)[L], int g,
                                              float (&acc)[Chunk<T>::E])

@@ -100,7 +100,14 @@ int64_t msda_launch_count(int reset);
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
  *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
  *                    2 row kernel + on-SM aggregation of the coarse levels (msda_bwd_binned) |
- *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems)
+ *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems) |
+ *                    4 planes: one kernel; the coarse levels' grad_value accumulated in shared memory as int32 fixed
+ *                    point (native ATOMS.ADD, per-item power-of-two scale from a rigorous bound), fine levels by reds
+ *   "planes_rows"    planes backward: query rows per work item / CTA (default 1024)
+ *   "planes_threads" planes backward CTA size: 512 | 768 (default) | 1024
+ *   "planes_budget"  planes backward A/B: cap in bytes on the shared-memory planes (-1 = all; 0 = every level by reds)
+ *   "planes_auto"    auto rule: 1 (default) = mode 4 for dense D=32 problems in bf16 or whose three coarse levels
+ *                    (~S/4 pixels) fit in shared memory; 0 = never
  *   "staged_min_rows" see "variant"   (default 200)
  *   "staged_rows"    staged forward: query rows per work item / CTA (default 1024)
  *   "staged_persistent" staged forward A/B: 1 = one CTA per SM walking the items round-robin instead of one CTA per item
@@ -124,7 +131,9 @@ size_t msda_backward_workspace_bytes(const msda_dims *dims, int dtype, unsigned 
  *   1  row kernel: every tap is a global vector red into a zero-filled grad_value (or workspace);
  *   2  row kernel for the fine levels + msda_bwd_binned: coarse levels aggregated in shared memory, flushed once;
  *   3  row kernel for grad_sampling_loc / grad_attn_weight + msda_bwd_owned: every grad_value line is written exactly
- *      once by its owner -- no zero-fill (MSDA_FLAG_ZERO_GRAD_VALUE costs nothing), no workspace, no fold.
+ *      once by its owner -- no zero-fill (MSDA_FLAG_ZERO_GRAD_VALUE costs nothing), no workspace, no fold;
+ *   4  msda_bwd_planes: the row algorithm in one kernel whose coarse-level taps are integer shared-memory atomics into
+ *      per-(image, head) fixed-point planes flushed once per work item; the other levels leave as vector reds.
  * A pure function of (dims, dtype, flags) and the msda_set_tuning knobs. */
 int msda_backward_strategy(const msda_dims *dims, int dtype, unsigned flags);
 

@@ -37,8 +37,13 @@ def main():
     ap.add_argument("--loc-dist", default="uniform")
     ap.add_argument("--modes", default="1,2,3")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--tuning", default="", help="extra msda_set_tuning knobs for the whole run: key=value,key=value")
+    ap.add_argument("--skip-fwd", action="store_true")
     args = ap.parse_args()
     lib = _lib.load()
+    for kv in filter(None, args.tuning.split(",")):
+        k, v = kv.split("=")
+        _lib.set_tuning(k, int(v))
     dev = torch.device("cuda", 0)
     peak, _ = bench.hbm_peak()
     results = {}
@@ -88,7 +93,7 @@ def main():
             return a.elapsed_time(b) / args.iters
 
         res = {"N": N, "Lq": Lq, "S": S, "D": D, "dtype": cfg["dtype"], "fwd_alg_MB": fb / 1e6, "bwd_alg_MB": bb / 1e6}
-        for variant in (0, 5, 3):
+        for variant in (() if args.skip_fwd else (0, 5, 3)):
             prev = _lib.set_tuning("variant", variant)
             try:
                 ms = timeit(fwd)

@@ -1,8 +1,8 @@
 """GPU: element-wise parity at the FULL sizes of BASELINE.json's configs, through the C ABI with the
 default (auto) kernel selection -- so the shapes the bench measures are the shapes that are checked:
 
-  config 3  encoder 800x1333, Lq = S = 22223, D = 32     -> fwd_v5, bwd_v5
-  config 2  encoder 384x640,  Lq = S = 5100,  D = 32     -> fwd_staged (three of four levels fit on chip), bwd_v5
+  config 3  encoder 800x1333, Lq = S = 22223, D = 32     -> fwd_v5, bwd_v5 (fp32) / bwd_planes (bf16)
+  config 2  encoder 384x640,  Lq = S = 5100,  D = 32     -> fwd_staged (three of four levels fit on chip), bwd_planes
   config 4  decoder Lq = 150, D = 64, S = 22223 / 5100   -> fwd_v5, bwd_v5 + msda_bwd_owned (forced here: the auto rule
             picks it for bf16 problems whose grad_value is >= 64 MB, i.e. at the bench batch sizes, not at N = 2)
 (the binned backward, not a default, is forced in a second pass over the two encoder shapes)
@@ -56,10 +56,15 @@ def padding_mask(N, shapes, frac=0.1):
 
 FULL_SIZE = [
     # id,                 pyramid,                   Lq,   D,  expected backward kernel substring
-    ("enc800x1333_d32", helpers.PYRAMID_800x1333, None, 32, "bwd_v5<"),
-    ("enc384x640_d32", helpers.PYRAMID_384x640, None, 32, "bwd_v5<"),
+    ("enc800x1333_d32_row", helpers.PYRAMID_800x1333, None, 32, "bwd_v5<"),
+    ("enc384x640_d32_row", helpers.PYRAMID_384x640, None, 32, "bwd_v5<"),
+    ("enc800x1333_d32_auto", helpers.PYRAMID_800x1333, None, 32, "auto"),   # fp32: row kernel, bf16: planes
+    ("enc384x640_d32_auto", helpers.PYRAMID_384x640, None, 32, "bwd_planes"),  # three gradient planes fit on chip
     ("enc800x1333_d32_binned", helpers.PYRAMID_800x1333, None, 32, "+binned"),
     ("enc384x640_d32_binned", helpers.PYRAMID_384x640, None, 32, "+binned"),
+    ("enc800x1333_d32_planes", helpers.PYRAMID_800x1333, None, 32, "bwd_planes"),
+    ("enc384x640_d32_planes", helpers.PYRAMID_384x640, None, 32, "bwd_planes"),
+    ("enc384x640_d64_planes", helpers.PYRAMID_384x640, None, 64, "bwd_planes"),
     ("dec800x1333_d64", helpers.PYRAMID_800x1333, 150, 64, "+owned"),
     ("dec384x640_d64", helpers.PYRAMID_384x640, 150, 64, "+owned"),
     ("dec800x1333_d32", helpers.PYRAMID_800x1333, 150, 32, "+owned"),
@@ -81,12 +86,15 @@ def test_full_size_elementwise_vs_oracle(lib, oracle, name, shapes, Lq, D, bsub,
     # masked pixels are zero rows of value (reference modules/ms_deform_attn.py:96-97)
     case["value"][padding_mask(N, shapes)] = 0.0
     case = helpers.rounded_case(case, dtype)
-    prev = lib.set_tuning("bwd_mode", 2 if name.endswith("_binned") else 3 if bsub == "+owned" else 0)
+    prev = lib.set_tuning("bwd_mode", 2 if name.endswith("_binned") else 4 if name.endswith("_planes") else
+                          1 if name.endswith("_row") else 3 if bsub == "+owned" else 0)
+    if bsub == "auto":
+        bsub = "bwd_planes" if dtype == torch.bfloat16 else "bwd_v5<"
     try:
         got = run_kernels(lib, case, dtype)
     finally:
         lib.set_tuning("bwd_mode", prev)
-    if name.startswith("enc384x640"):
+    if name.startswith("enc384x640") and D == 32:
         expect = "fwd_staged"  # auto rule: D=32, coarse levels (~S/4 pixels) fit in shared memory
     else:
         expect = "fwd_v5"

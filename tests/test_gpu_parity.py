@@ -163,6 +163,8 @@ KERNEL_VARIANTS = [  # (msda_set_tuning settings, expected forward-kernel prefix
     ({"variant": 3, "v3_threads": 512, "bwd_mode": 2}, "fwd_staged", "+binned"),
     ({"variant": 3, "v3_threads": 1024, "bwd_mode": 3}, "fwd_staged", "+owned"),
     ({"variant": 3, "v3_threads": 768, "bwd_mode": 0}, "fwd_staged", "bwd_v5"),
+    ({"variant": 5, "bwd_mode": 4, "planes_rows": 64}, "fwd_v5", "bwd_planes"),
+    ({"variant": 5, "bwd_mode": 4, "planes_threads": 768, "planes_rows": 1024}, "fwd_v5", "bwd_planes"),
     ({"variant": 0, "staged_min_rows": 1, "bwd_mode": 0, "bin_min_rows": 64}, "fwd_", "bwd_v5"),
 ]
 
@@ -186,7 +188,7 @@ def test_every_kernel_variant_matches_oracle(lib, oracle, tuning, fprefix, bsub,
     assert_parity(got, oracle_results(oracle, case), case, dtype, str(tuning))
 
 
-BWD_MODES = {"row": 1, "binned": 2, "owned": 3}
+BWD_MODES = {"row": 1, "binned": 2, "owned": 3, "planes": 4}
 
 
 def run_backward_mode(lib, case, dtype, mode, accumulate_into=None):
@@ -220,7 +222,7 @@ def run_backward_mode(lib, case, dtype, mode, accumulate_into=None):
     return dict(grad_value=gv, grad_loc=gl, grad_attn=ga, bwd_kernel=name)
 
 
-@pytest.mark.parametrize("mode", ["binned", "owned"])
+@pytest.mark.parametrize("mode", ["binned", "owned", "planes"])
 @pytest.mark.parametrize("dtype,D", [(torch.float32, 32), (torch.float32, 64), (torch.bfloat16, 32), (torch.bfloat16, 64)])
 @pytest.mark.parametrize("shapes,Lq", [
     ([(40, 60), (20, 30), (10, 15), (5, 8)], 1300),   # several query tiles per item, every level class
@@ -232,7 +234,7 @@ def test_aggregating_backward_strategies_vs_oracle(lib, oracle, mode, dtype, D, 
     sort by pixel, every grad_value line stored once) against the fp64 oracle, incl. out-of-range samples."""
     case = helpers.rounded_case(helpers.make_inputs(3, Lq, 8, D, shapes, 4, seed=31 + Lq, lo=-0.3, hi=1.3), dtype)
     got = run_backward_mode(lib, case, dtype, mode)
-    assert ("+" + mode) in got["bwd_kernel"], got["bwd_kernel"]
+    assert ("bwd_planes" if mode == "planes" else "+" + mode) in got["bwd_kernel"], got["bwd_kernel"]
     ref = oracle_results(oracle, case)
     _, gtol = TOL[dtype]
     assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref["grad_value"]) <= gtol
@@ -243,7 +245,7 @@ def test_aggregating_backward_strategies_vs_oracle(lib, oracle, mode, dtype, D, 
     assert max_norm_err(got["grad_value"].double().cpu().numpy(), row["grad_value"].double().cpu().numpy()) <= gtol
 
 
-@pytest.mark.parametrize("mode", ["binned", "owned"])
+@pytest.mark.parametrize("mode", ["binned", "owned", "planes"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_aggregating_backward_accumulates_into_grad_value(lib, oracle, mode, dtype):
     """Without MSDA_FLAG_ZERO_GRAD_VALUE the backward adds to what grad_value holds (include/msda.h), whichever strategy."""
@@ -261,7 +263,7 @@ def test_nonfinite_gradients_propagate_through_aggregating_strategies(lib):
     shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
     case = helpers.make_inputs(1, 64, 8, 32, shapes, 4, seed=4, dtype=np.float32)
     case["grad_out"][0, 5, :32] = np.nan
-    for mode in ("row", "binned", "owned"):
+    for mode in ("row", "binned", "owned", "planes"):
         got = run_backward_mode(lib, case, torch.float32, mode)
         gv = got["grad_value"][0, :, 0]
         assert torch.isnan(gv).any(), mode
@@ -950,15 +952,18 @@ def test_host_submit_wait_pipelines_several_calls(lib, oracle):
 
 
 def test_backward_strategy_selection_for_the_baseline_configs(lib):
-    """msda_backward_strategy (include/msda.h): the automatic choice for BASELINE.json's shapes -- 1 = row reds, 3 = owned."""
+    """msda_backward_strategy (include/msda.h): the automatic choice for BASELINE.json's shapes -- 1 = row reds, 3 = owned,
+    4 = planes."""
     import ctypes
     raw = lib.load()
     S_big, S_small = 22223, 5100
     pick = lambda n, s, d, lq, dt, flags=0: raw.msda_backward_strategy(
         ctypes.byref(lib.MsdaDims(n, s, 8, d, 4, lq, 4)), lib._DTYPE_CODE[dt], flags)
     assert pick(16, S_big, 32, S_big, torch.float32) == 1     # config 3: dense encoder -> row kernel
-    assert pick(32, S_small, 32, S_small, torch.float32) == 1  # config 2
-    assert pick(32, S_big, 32, S_big, torch.bfloat16) == 1     # config 5, encoder half: dense -> row kernel
+    assert pick(32, S_small, 32, S_small, torch.float32) == 4  # config 2: three gradient planes fit on chip -> planes
+    assert pick(32, S_big, 32, S_big, torch.bfloat16) == 4     # config 5, encoder half: dense bf16 -> planes
+    assert pick(32, S_big, 32, S_big, torch.bfloat16, lib.FLAG_DETERMINISTIC) == 1
+    assert pick(1, S_small, 32, 1000, torch.float32) == 1      # too few rows to fill the machine
     assert pick(32, S_big, 64, 150, torch.bfloat16) == 3       # config 4 / 5, decoder half in bf16 -> owned
     assert pick(64, S_small, 64, 150, torch.bfloat16) == 3
     assert pick(64, S_small, 64, 150, torch.float32) == 1      # GRIT's fp32 decoder: both strategies tie, row kept
