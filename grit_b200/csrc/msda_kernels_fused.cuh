@@ -21,12 +21,14 @@
 
 namespace msda {
 
+// Maximum over the row's L*P logits.  Every lane of the warp works on the same row (lanes >= LP mirror lanes < LP), so
+// this is a full-warp maximum: one sm_100a `redux.sync.max.f32` (CREDUX.MAX.F32) instead of log2(LP) shuffle + max steps.
 template <int LP>
 __device__ __forceinline__ float segment_max(float v)
 {
-#pragma unroll
-    for (int off = LP / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
-    return v;
+    float m;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+    return m;
 }
 template <int LP>
 __device__ __forceinline__ float segment_sum(float v)
@@ -62,27 +64,52 @@ __device__ __forceinline__ float4 load_ref(const float *__restrict__ ref, const 
     return rf;
 }
 
-// Softmax weight and sampling location of point `rp` of row `row`, from the Linears' raw outputs.
+// 2^x for x <= 0 (softmax numerators): one MUFU.EX2 instead of exp2f's range-scaling sequence; results below the
+// smallest normal flush to zero, which a softmax weight of < 1e-38 may.
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Softmax weight and sampling location of point `rp` of row `row`, from the Linears' raw outputs.  inv_w / inv_h are the
+// reciprocals of the level's size, computed once per CTA (stage_levels_inv): with three IEEE divisions per lane and row
+// (two normalisers and the softmax denominator, ~15 instructions each) the fused kernels executed a fifth more
+// instructions than the plain ones and were that much slower (profiles/r02_fused_ab.json: 1.52 vs 1.27 ms forward).
 template <int L, int P, int RD>
 __device__ __forceinline__ void fused_point(const float *__restrict__ offs, const float *__restrict__ logits,
                                             const float *__restrict__ ref, const float *__restrict__ vratio, int n,
                                             int64_t row, int64_t bq, int rp, int rl,
-                                            int H, int W, float &a_soft, float &x, float &y)
+                                            float inv_h, float inv_w, float &a_soft, float &x, float &y)
 {
     constexpr int LP = L * P;
     const float lg = __ldg(logits + row * LP + rp);
-    const float mx = segment_max<LP>(lg);
-    const float ex = exp2f((lg - mx) * 1.4426950408889634f);
-    a_soft = ex / segment_sum<LP>(ex);
     const float2 of = __ldg(reinterpret_cast<const float2 *>(offs) + row * LP + rp);
     const float4 rf = load_ref<L, RD>(ref, vratio, bq, n, rl);
+    const float mx = segment_max<LP>(lg);
+    const float ex = ex2_approx((lg - mx) * 1.4426950408889634f);
+    a_soft = __fdividef(ex, segment_sum<LP>(ex));  // denominator in [1, LP]: MUFU.RCP + FMUL, 2 ulp
     if (RD == 2) {
-        x = rf.x + of.x / (float)W;
-        y = rf.y + of.y / (float)H;
+        x = fmaf(of.x, inv_w, rf.x);
+        y = fmaf(of.y, inv_h, rf.y);
     } else {
-        x = rf.x + of.x / (float)P * rf.z * 0.5f;
-        y = rf.y + of.y / (float)P * rf.w * 0.5f;
+        x = fmaf(of.x * (0.5f / (float)P), rf.z, rf.x);
+        y = fmaf(of.y * (0.5f / (float)P), rf.w, rf.y);
     }
+}
+
+template <int L>
+__device__ __forceinline__ void stage_levels_inv(const int64_t *shapes, const int64_t *lsi, int (&sH)[L], int (&sW)[L],
+                                                 int (&sStart)[L], float (&sInvH)[L], float (&sInvW)[L])
+{
+    if (threadIdx.x < L) {
+        const int h = (int)shapes[2 * threadIdx.x], w = (int)shapes[2 * threadIdx.x + 1];
+        sH[threadIdx.x] = h, sW[threadIdx.x] = w;
+        sInvH[threadIdx.x] = 1.f / (float)h, sInvW[threadIdx.x] = 1.f / (float)w;
+        sStart[threadIdx.x] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
 }
 
 template <typename T, int D, int L, int P, int WARPS, int RD>
@@ -98,7 +125,8 @@ msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     static_assert(D % E == 0 && 32 % LPT == 0 && LP % G == 0 && LP <= 32 && 32 % LP == 0, "unsupported");
 
     __shared__ int sH[L], sW[L], sStart[L];
-    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+    __shared__ float sInvH[L], sInvW[L];
+    stage_levels_inv<L>(shapes, lsi, sH, sW, sStart, sInvH, sInvW);
 
     const int lane = threadIdx.x & 31;
     const int g = lane / LPT, sub = lane % LPT;
@@ -115,7 +143,7 @@ msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const int rp = lane % LP;
     const int rl = rp / P;
     float a_soft, x, y;
-    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sInvH[rl], sInvW[rl], a_soft, x, y);
     const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
 
     float acc[E];
@@ -150,7 +178,8 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     static_assert(PPG <= LPT && (PPG & (PPG - 1)) == 0, "halving reduction needs PPG to be a power of two <= LPT");
 
     __shared__ int sH[L], sW[L], sStart[L];
-    stage_levels<L>(shapes, lsi, sH, sW, sStart);
+    __shared__ float sInvH[L], sInvW[L];
+    stage_levels_inv<L>(shapes, lsi, sH, sW, sStart, sInvH, sInvW);
 
     const int lane = threadIdx.x & 31;
     const int g = lane / LPT, sub = lane % LPT;
@@ -172,7 +201,7 @@ msda_bwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
     const int rp = lane % LP;
     const int rl = rp / P;
     float a_soft, x, y;
-    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sH[rl], sW[rl], a_soft, x, y);
+    fused_point<L, P, RD>(offs, logits, ref, vratio, (int)blockIdx.y, row, bq, rp, rl, sInvH[rl], sInvW[rl], a_soft, x, y);
     const Resolved mine = resolve_point_v(x, y, sH[rl], sW[rl], sStart[rl], a_soft);
 
     float go[E];

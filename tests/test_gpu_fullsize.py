@@ -116,3 +116,39 @@ def test_full_size_backward_strategies_agree(lib):
     assert "+binned" in binned["bwd_kernel"] and "+binned" not in row["bwd_kernel"]
     assert torch.equal(row["grad_loc"], binned["grad_loc"]) and torch.equal(row["grad_attn"], binned["grad_attn"])
     assert max_norm_err(binned["grad_value"].double().cpu().numpy(), row["grad_value"].double().cpu().numpy()) < 2e-5
+
+
+def test_fused_forward_full_size_error_vs_fp64_matches_the_unfused_path(lib, oracle):
+    """800x1333, fp32: the fused forward takes raw offsets / logits / reference points and forms the sampling locations
+    with reciprocal multiplies (no IEEE divisions in the kernel); the unfused path gets locations PyTorch computed with
+    divisions.  Both hold fp32 locations -- one ulp of a location is ~1e-5 px on a 167-px-wide level -- so both sit a few
+    1e-6 from the fp64 truth; the fused path must not be further from it than the unfused one by more than that noise."""
+    from .conftest import max_norm_err
+    rng = np.random.default_rng(5)
+    shapes_l = helpers.PYRAMID_800x1333
+    N, M, D, L, P = 1, 8, 32, 4, 4
+    S = sum(h * w for h, w in shapes_l)
+    Lq = S
+    value = rng.standard_normal((N, S, M, D)).astype(np.float32)
+    offs = (rng.standard_normal((N, Lq, M, L, P, 2)) * 2.0).astype(np.float32)
+    logits = rng.standard_normal((N, Lq, M, L * P)).astype(np.float32)
+    ref = (rng.random((N, Lq, L, 2)) * 1.1 - 0.05).astype(np.float32)
+    shp = np.asarray(shapes_l, dtype=np.float64)
+    norm = np.stack([shp[:, 1], shp[:, 0]], -1)[None, None, None, :, None, :]
+    loc64 = ref.astype(np.float64)[:, :, None, :, None, :] + offs.astype(np.float64) / norm
+    attn64 = oracle.softmax_np(logits.astype(np.float64), -1).reshape(N, Lq, M, L, P)
+    shapes_np = np.asarray(shapes_l, dtype=np.int64)
+    lsi = helpers.level_start(shapes_l)
+    truth = oracle.forward(value, shapes_np, lsi, loc64, attn64)
+
+    cu = lambda x: torch.from_numpy(x).cuda()
+    fused = lib.fused_forward(cu(value), cu(shapes_np), cu(lsi), cu(offs), cu(logits), cu(ref))
+    assert lib.last_kernel().startswith("fwd_fused")
+    t_ref, t_off = cu(ref), cu(offs)
+    loc32 = (t_ref[:, :, None, :, None, :] + t_off / cu(norm.astype(np.float32))).contiguous()
+    attn32 = torch.softmax(cu(logits), -1).view(N, Lq, M, L, P).contiguous()
+    plain = lib.forward(cu(value), cu(shapes_np), cu(lsi), loc32, attn32)
+    e_fused = max_norm_err(fused.double().cpu().numpy().reshape(truth.shape), truth)
+    e_plain = max_norm_err(plain.double().cpu().numpy().reshape(truth.shape), truth)
+    assert e_fused < 1e-5 and e_plain < 1e-5, (e_fused, e_plain)
+    assert e_fused <= 2.0 * e_plain + 1e-6, (e_fused, e_plain)
