@@ -51,7 +51,8 @@ class _nvtx_range:
 
 
 def library_path() -> str:
-    return _build.LIB_PATH
+    """The in-tree library; GRIT_B200_LIB names another build of the same ABI (same-box A/B of two kernel versions)."""
+    return os.environ.get("GRIT_B200_LIB") or _build.LIB_PATH
 
 
 def load():

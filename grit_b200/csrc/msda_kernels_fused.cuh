@@ -113,7 +113,7 @@ __device__ __forceinline__ void stage_levels_inv(const int64_t *shapes, const in
 }
 
 template <typename T, int D, int L, int P, int WARPS, int RD>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (sizeof(T) == 2 ? 1280 : 1536) / (WARPS * 32))  // as msda_fwd_v5
 msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
                const float *__restrict__ vratio, T *__restrict__ out, int S, int M, int Lq, unsigned rows_per_image)

@@ -125,13 +125,45 @@ __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg
         const float lw = __shfl_sync(0xffffffffu, mine.lw, pt);
         const int o0 = (pm >> 4) * MD, o1 = o0 + MD;
         const int o2 = o0 + sW[pt / P] * MD, o3 = o2 + MD;
-        float v0[E], v1[E], v2[E], v3[E];
-        load_taps<T, Chunk<T>, ALL>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
         const float ah = a - a * lh, al = a * lh, hw = 1.f - lw;
         const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
+        if (ALL) {
+            float v0[E], v1[E], v2[E], v3[E];
+            load_taps<T, Chunk<T>, true>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-            acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+            for (int e = 0; e < E; ++e)
+                acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+        } else {
+            // General path, fp32: one predicated block per tap -- the load directly followed by its FMAs under the tap's
+            // predicate -- so nothing is zero-filled (that was 8 CS2R per iteration, and 62 % of the rows of an 800x1333
+            // pyramid take this path with uniform locations because some point of the row touches a border).  Same-box
+            // A/B at 800x1333 (profiles/r02_fwd_general_path_ab.txt): zero-fill 1.31 ms, this form 1.24 ms; the four
+            // predicated loads first and the FMAs after them 1.34 ms, and the same blocks behind a helper function
+            // 1.30 ms (ptxas then spills one register at the 40-register budget).  bf16 keeps the zero-fill form: its
+            // predicated blocks measured 3.21 vs 2.68 ms.
+            if constexpr (E > 4) {
+                float v0[E], v1[E], v2[E], v3[E];
+                load_taps<T, Chunk<T>, false>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
+                continue;
+            }
+            {
+                if (pm & 8) { float v[E]; Chunk<T>::load(vimg + o3, v);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(w3, v[e], acc[e]); }
+                if (pm & 4) { float v[E]; Chunk<T>::load(vimg + o2, v);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(w2, v[e], acc[e]); }
+                if (pm & 2) { float v[E]; Chunk<T>::load(vimg + o1, v);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(w1, v[e], acc[e]); }
+                if (pm & 1) { float v[E]; Chunk<T>::load(vimg + o0, v);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[e] = fmaf(w0, v[e], acc[e]); }
+            }
+        }
     }
 }
 
@@ -185,7 +217,7 @@ __device__ __forceinline__ void fwd_row_body_hoisted(const Resolved &mine, const
 // (40 registers, 12 CTAs per SM.  A 32-register build -- __launch_bounds__(128, 16), 64 resident warps -- spills and
 //  measured 1.38 vs 1.31 ms; naming a minimum of ONE CTA per SM makes ptxas spend 92 registers and costs 35 %.)
 template <typename T, int D, int L, int P, int WARPS, bool HOIST = false>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (HOIST ? 1024 : sizeof(T) == 2 ? 1280 : 1536) / (WARPS * 32))  // fp32 <= 40 registers (48 resident warps), bf16 <= 48 (40 warps)
 msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int M,
             unsigned rows_per_image)
