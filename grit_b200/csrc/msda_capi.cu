@@ -87,7 +87,11 @@ std::atomic<int> g_planes_auto{1};        // auto: 0 = never choose the planes b
 std::atomic<int> g_planes_budget{-1};     // planes backward A/B: cap on the plane bytes (-1 = all the shared memory)
 std::atomic<int> g_staged_rows{1024};     // staged forward: query rows per work item (CTA)
 std::atomic<int> g_staged_persistent{0};  // staged forward A/B: 1 = one CTA per SM walking the items round-robin
-std::atomic<int> g_staged_min_rows{200};  // auto: staged forward (D=32) when num_heads*num_query / #SMs >= this
+std::atomic<int> g_staged_auto{0};        // auto: 1 = let the rule below choose the staged forward; 0 (default) = never:
+                                          // since the row kernel's general path stopped zero-filling (1.31 -> 1.24 ms)
+                                          // it beats the staged forward on every shape measured (0.59 vs 0.60 ms at
+                                          // 384x640, 1.22 vs 1.38 ms at 800x1333; profiles/r02_fwd_general_path_ab.txt)
+std::atomic<int> g_staged_min_rows{200};  // staged rule: D=32, coarse levels fit, num_heads*num_query / #SMs >= this
 std::atomic<int> g_bin_min_rows{0};      // auto: binned coarse levels when num_query >= this; 0 = never (measured slower
                                          // than the plain row kernel on B200)
 std::atomic<int> g_owned_max_taps{4};    // auto: owned when taps per value pixel (Lq*L*P*4 / S) <= this
@@ -573,6 +577,7 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
     if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
     if (key && !strcmp(key, "staged_min_rows")) knob = &g_staged_min_rows;
+    if (key && !strcmp(key, "staged_auto")) knob = &g_staged_auto;
     if (key && !strcmp(key, "staged_rows")) knob = &g_staged_rows;
     if (key && !strcmp(key, "staged_persistent")) knob = &g_staged_persistent;
     if (key && !strcmp(key, "owned_max_taps")) knob = &g_owned_max_taps;
@@ -608,13 +613,14 @@ int msda_forward(const void *value, const int64_t *spatial_shapes, const int64_t
     bool done = false;
     if (vec_eligible(dims, dtype, flags) && aligned16(value) && aligned16(output) &&
         (reinterpret_cast<uintptr_t>(sampling_loc) & 7u) == 0) {
-        // The staged forward pays off when at least three of the four levels of a head fit in shared memory, i.e. >= 3/4
-        // of the taps come from the SM (measured, profiles/r02_staged_ab.txt: 0.60 vs 0.62 ms at 384x640 fp32); with two
-        // levels on chip (800x1333: 1.34 vs 1.31 ms) or one (D=64) the row kernel wins.  The host does not read
-        // spatial_shapes, so the rule assumes the usual 4:1 pyramid: all levels but the finest hold ~S/4 pixels.
+        // The staged forward paid off when at least three of the four levels of a head fit in shared memory, i.e. >= 3/4
+        // of the taps come from the SM (profiles/r02_staged_ab.txt: 0.60 vs 0.62 ms at 384x640 fp32) -- until the row
+        // kernel's general path lost its zero-fill (0.59 ms there now), so the rule is opt-in ("staged_auto").  The host
+        // does not read spatial_shapes, so the rule assumes the usual 4:1 pyramid: all levels but the finest hold ~S/4
+        // pixels.
         const int variant = g_variant.load();
         const int64_t coarse_bytes = dims->spatial_size / 4 * dims->channels * (int64_t)dtype_size(dtype);
-        const bool staged_auto = variant == 0 && dims->channels == 32 && dims->num_levels >= 3 &&
+        const bool staged_auto = variant == 0 && g_staged_auto.load() && dims->channels == 32 && dims->num_levels >= 3 &&
                                  coarse_bytes <= device_info().max_smem_optin - 2048 &&
                                  dims->num_heads * dims->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms;
         if (variant == 3 || staged_auto) {

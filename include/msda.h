@@ -92,9 +92,11 @@ const char *msda_last_kernel(void);
 int64_t msda_launch_count(int reset);
 
 /* Tuning / A-B testing knob (process-wide; for benchmarks and tests).  Keys:
- *   "variant"        forward: 0 auto (default: the staged forward for D=32 problems whose coarse levels -- ~S/4 pixels of
- *                    a 4:1 pyramid -- fit in shared memory and that have >= "staged_min_rows" (head, query) rows per
- *                    image per SM; else the row kernel) | 5 lean row kernel | 3 shared-memory-staged forward
+ *   "variant"        forward: 0 auto (default: the row kernel; with "staged_auto" = 1 the staged forward for D=32
+ *                    problems whose coarse levels -- ~S/4 pixels of a 4:1 pyramid -- fit in shared memory and that have
+ *                    >= "staged_min_rows" (head, query) rows per image per SM) | 5 lean row kernel |
+ *                    3 shared-memory-staged forward
+ *   "staged_auto"    0 (default) | 1: see "variant" (the row kernel measured faster on every shape since round 2)
  *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
  *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)

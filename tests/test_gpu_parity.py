@@ -165,7 +165,7 @@ KERNEL_VARIANTS = [  # (msda_set_tuning settings, expected forward-kernel prefix
     ({"variant": 3, "v3_threads": 768, "bwd_mode": 0}, "fwd_staged", "bwd_v5"),
     ({"variant": 5, "bwd_mode": 4, "planes_rows": 64}, "fwd_v5", "bwd_planes"),
     ({"variant": 5, "bwd_mode": 4, "planes_threads": 768, "planes_rows": 1024}, "fwd_v5", "bwd_planes"),
-    ({"variant": 0, "staged_min_rows": 1, "bwd_mode": 0, "bin_min_rows": 64}, "fwd_", "bwd_v5"),
+    ({"variant": 0, "staged_auto": 1, "staged_min_rows": 1, "bwd_mode": 0, "bin_min_rows": 64}, "fwd_", "bwd_v5"),
 ]
 
 
