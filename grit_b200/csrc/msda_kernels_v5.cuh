@@ -140,7 +140,8 @@ __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg
             // A/B at 800x1333 (profiles/r02_fwd_general_path_ab.txt): zero-fill 1.31 ms, this form 1.24 ms; the four
             // predicated loads first and the FMAs after them 1.34 ms, and the same blocks behind a helper function
             // 1.30 ms (ptxas then spills one register at the 40-register budget).  bf16 keeps the zero-fill form: its
-            // predicated blocks measured 3.21 vs 2.68 ms.
+            // predicated blocks measured 3.21 vs 2.68 ms, and predicated raw loads
+            // (inline PTX) followed by predicated unpack + FMA blocks 2.81 ms.
             if constexpr (E > 4) {
                 float v0[E], v1[E], v2[E], v3[E];
                 load_taps<T, Chunk<T>, false>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
