@@ -275,7 +275,8 @@ def workload_config(args, cfg, world):
                          "concentrated": "diagnostic: all samples in a 2% window (L1-resident taps)"}[args.loc_dist],
             "l2_policy": "inputs larger than L2: every layer reads its own input set (>= 1 GB at the default workload), "
                          "126 MB L2 is cycled between launches",
-            "parallelism": f"batch-sharded replicas x{world}"}
+            "parallelism": f"batch-sharded replicas x{world}",
+            **({"tuning": args.tuning} if args.tuning else {})}
 
 
 def main():
@@ -289,6 +290,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--tuning", default="", help="A/B only: msda_set_tuning knobs for the whole run, key=value,key=value "
+                                                 "(recorded in config.tuning; the line of record is run without it)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--e2e-chunk", type=int, default=None, help="images per pipeline chunk of the host-buffer path")
     args = ap.parse_args()
@@ -316,6 +319,8 @@ def main():
     numa_note = bind_to_gpu_numa_node(local_rank) if world > 1 and os.environ.get("MSDA_BENCH_NUMA_BIND", "1") == "1" \
         else None
     lib = _lib.load()  # raises if the CUDA library is missing: no fallback
+    for kv in filter(None, args.tuning.split(",")):
+        _lib.set_tuning(kv.split("=")[0], int(kv.split("=")[1]))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device")
     torch.cuda.set_device(local_rank)
@@ -574,7 +579,10 @@ def main():
             achieved = taps / (avg_ms * 1e-3) / 1e9
             roof["on_chip"] = {
                 "resource": {"gather": "L2->L1 gather of random 128-byte lines (LDG.E.128 stream)",
-                             "red": "L2 reduction of random 128-byte lines (REDG.E.ADD.F32x4 stream)"}[which],
+                             "red": "L2 reduction of random 128-byte lines (REDG.E.ADD.F32x4 stream)"
+                                    + ("; bwd_planes sends the smallest levels' taps to shared-memory integer atomics "
+                                       "instead, so its tap rate is not capped by this ceiling"
+                                       if (kernel_names[1] or "").startswith("bwd_planes") else "")}[which],
                 "ceiling_glines_per_s": ceiling, "achieved_glines_per_s": achieved, "frac": achieved / ceiling,
                 "how": "msda_probe_ceiling microbenchmark, same access pattern, no arithmetic, measured in this run"}
         del region

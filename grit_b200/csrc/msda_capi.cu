@@ -81,10 +81,10 @@ std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
                                       //           | 4 planes (coarse levels in shared-memory int32 fixed point)
-std::atomic<int> g_planes_rows{1024};     // planes backward: query rows per work item (CTA)
-std::atomic<int> g_planes_threads{768};  // planes backward CTA size: 512, 768 or 1024
+std::atomic<int> g_planes_rows{0};        // planes backward: query rows per work item (CTA); 0 = 256 for small CTAs, 1024 otherwise
+std::atomic<int> g_planes_threads{768};  // planes backward CTA size: 256 (x4 per SM), 512, 768 or 1024 (one per SM)
 std::atomic<int> g_planes_auto{1};        // auto: 0 = never choose the planes backward by default
-std::atomic<int> g_planes_budget{-1};     // planes backward A/B: cap on the plane bytes (-1 = all the shared memory)
+std::atomic<int> g_planes_budget{1 << 30};  // planes backward: cap on the plane bytes (default: all the shared memory)
 std::atomic<int> g_staged_rows{1024};     // staged forward: query rows per work item (CTA)
 std::atomic<int> g_staged_persistent{0};  // staged forward A/B: 1 = one CTA per SM walking the items round-robin
 std::atomic<int> g_staged_auto{0};        // auto: 1 = let the rule below choose the staged forward; 0 (default) = never:
@@ -124,6 +124,7 @@ bool vec_eligible(const msda_dims *d, int dtype, unsigned flags)
 struct DeviceInfo {
     int sms = 0;
     int max_smem_optin = 0;
+    int smem_per_sm = 0;
 };
 
 const DeviceInfo &device_info()
@@ -135,6 +136,7 @@ const DeviceInfo &device_info()
     if (d.sms == 0) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     }
     return d;
 }
@@ -425,16 +427,16 @@ int choose_bwd_mode(const msda_dims *d, int dtype, unsigned flags)
         return BWD_OWNED;
     const int bin_min = g_bin_min_rows.load();
     if (can_bin && bin_min > 0 && d->num_levels >= 2 && d->num_query >= bin_min) return BWD_BINNED;
-    // planes (coarse levels accumulated in shared memory as int32 fixed point) where it measured faster than the row
-    // kernel (profiles/r02_planes_*.json): dense D=32 problems with enough rows to fill the machine, when three of the
-    // four gradient planes fit in shared memory (384x640 class, -10 %; same 4:1-pyramid assumption as the staged
-    // forward: the host does not read spatial_shapes) or in bf16 (800x1333: -7 %).  At 800x1333 in fp32 with uniform
-    // locations both run at 3.5 ms, so the row kernel (plain fp32 sums) stays.
+    // planes (coarse levels' gradient accumulated in shared memory as int32 fixed point) beats the row kernel on every
+    // dense D=32 shape INSIDE a long step, where the GPU runs at its power cap (bench.py, six layers back to back;
+    // profiles/r02_planes_bench_ab.txt): 800x1333 fp32 step 30.2 -> 29.4 ms (uniform) / 31.5 -> 29.0 ms (detector-like),
+    // bf16 60.9 -> 56.2 ms, 384x640 13.7 -> 12.3 ms, with one 768-thread CTA per SM.  Four 256-thread CTAs per SM are
+    // faster when the kernel is timed alone (3.33 vs 3.51 ms) but draw more power: the clocks of the whole step drop
+    // (1815 vs 1940 MHz) and the step is slower (29.9 ms).  Dense = more taps than the owned strategy's domain, and
+    // enough rows to fill the machine.
     if (g_planes_auto.load() && d->channels == 32 && taps > (int64_t)g_owned_max_taps.load() * d->spatial_size &&
-        d->num_heads * d->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms) {
-        const int64_t coarse_plane_bytes = d->spatial_size / 4 * d->channels * 4;
-        if (dtype == MSDA_BF16 || coarse_plane_bytes <= device_info().max_smem_optin - 8192) return BWD_PLANES;
-    }
+        d->num_heads * d->num_query >= (int64_t)g_staged_min_rows.load() * device_info().sms)
+        return BWD_PLANES;
     return BWD_ROW;
 }
 
@@ -485,16 +487,37 @@ int bwd_planes_launch(const msda_dims *d, const void *value, const int64_t *shap
 {
     using CH = typename BwdChunk<T>::type;
     auto kernel = msda::msda_bwd_planes<T, CH, DD, LL, PP, TH>;
-    const int smem = (device_info().max_smem_optin - 2048 - (TH / 32) * DD * 4) & ~15;  // minus the static shared memory
+    int smem = (device_info().max_smem_optin - 2048 - (TH / 32) * DD * 4) & ~15;  // minus the static shared memory
     if (smem <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
+    const int cap = g_planes_budget.load();
+    // Small CTAs share the SM (1024 / TH of them, the occupancy of the row kernel): each takes its share of the SM's shared
+    // memory -- 55 KB at TH = 256 -- and the device-side plan puts the smallest levels that fit there (800x1333: level 3,
+    // a quarter of the taps; 384x640: levels 2 + 3, half of them).  One big CTA per SM holds more levels but runs at the
+    // mercy of instruction latency.
+    if (TH <= 256) {
+        const int per_cta = device_info().smem_per_sm / (1024 / TH) - 1024 /* reserved per CTA */ - (TH / 32) * DD * 4 - 256;
+        if (per_cta < smem) smem = per_cta & ~15;
+        // Ask only for what the planes will need: what a CTA does not take stays L1 (800x1333: 3.31 ms with 36 KB per
+        // CTA, 3.52 ms with the full 55 KB).  The host does not read spatial_shapes, so the need is estimated from S for
+        // the usual 4:1 pyramid -- the k smallest of four levels hold S/85, S/17, S/4 pixels -- plus 15 %; a pyramid that
+        // needs more than the estimate simply keeps fewer levels on chip (the device-side plan decides).
+        const double px1 = (double)d->spatial_size / 85.0;
+        int64_t want = 0;
+        for (double mult : {1.0, 5.0, 21.0}) {
+            const int64_t bytes = (int64_t)(px1 * mult * 1.15 + 8.0) * DD * 4;
+            if (bytes <= smem) want = bytes;
+        }
+        if (want > 0 && want < smem) smem = (int)((want + 15) & ~15);
+        if (cap >= 0 && cap < smem) smem = (cap + 15) & ~15;
+    }
     if (int rc = optin_smem(kernel, smem)) return rc;
     int rows_per_item = g_planes_rows.load();
+    if (rows_per_item <= 0) rows_per_item = TH <= 256 ? 256 : 1024;  // measured best for each CTA size
     if (rows_per_item < 64) rows_per_item = 64;
     int64_t chunks = (d->num_query + rows_per_item - 1) / rows_per_item;
     if (chunks < 1) chunks = 1;
     const int64_t items = d->batch * chunks * d->num_heads;
     if (items > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
-    const int cap = g_planes_budget.load();
     kernel<<<(unsigned)items, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
                                               (const T *)gout, gv_acc, (float *)gloc, (float *)gattn, (int)d->batch,
                                               (int)d->spatial_size, (int)d->num_heads, (int)d->num_query,
@@ -515,7 +538,9 @@ int launch_bwd_planes(const msda_dims *d, const void *value, const int64_t *shap
                    ? bwd_planes_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st) \
                : th >= 768                                                                                             \
                    ? bwd_planes_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st)  \
-                   : bwd_planes_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st);
+               : th >= 512                                                                                             \
+                   ? bwd_planes_launch<T, DD, LL, PP, 512>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st)  \
+                   : bwd_planes_launch<T, DD, LL, PP, 256>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st);
     MSDA_FOR_EACH_FLAGSHIP_SPEC(X)
 #undef X
     return -1;

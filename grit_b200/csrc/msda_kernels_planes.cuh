@@ -138,7 +138,7 @@ __device__ __forceinline__ void planes_row_body(const Resolved &mine, const T *v
 }
 
 template <typename T, typename CH, int D, int L, int P, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 1024 / THREADS : 1)  // small CTAs: several per SM, 64 registers
 msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                 const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
                 float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int N, int S,

@@ -105,11 +105,13 @@ int64_t msda_launch_count(int reset);
  *                    3 owned: every grad_value line written once by its owner, no zero-fill / workspace (sparse problems) |
  *                    4 planes: one kernel; the coarse levels' grad_value accumulated in shared memory as int32 fixed
  *                    point (native ATOMS.ADD, per-item power-of-two scale from a rigorous bound), fine levels by reds
- *   "planes_rows"    planes backward: query rows per work item / CTA (default 1024)
- *   "planes_threads" planes backward CTA size: 512 | 768 (default) | 1024
- *   "planes_budget"  planes backward A/B: cap in bytes on the shared-memory planes (-1 = all; 0 = every level by reds)
- *   "planes_auto"    auto rule: 1 (default) = mode 4 for dense D=32 problems in bf16 or whose three coarse levels
- *                    (~S/4 pixels) fit in shared memory; 0 = never
+ *   "planes_rows"    planes backward: query rows per work item / CTA (default 0 = 256 for 256-thread CTAs, else 1024)
+ *   "planes_threads" planes backward CTA size: 768 (default) | 512 | 1024: one CTA per SM holding every level that fits |
+ *                    256: four CTAs per SM, each with the smallest levels' planes (faster when timed alone, slower
+ *                    inside a long step at the power cap)
+ *   "planes_budget"  planes backward: cap in bytes on the shared-memory planes (default 2^30 = all; 0 = every level by reds)
+ *   "planes_auto"    auto rule: 1 (default) = mode 4 for dense D=32 problems (more than "owned_max_taps" taps per value
+ *                    pixel, >= "staged_min_rows" (head, query) rows per image per SM); 0 = never
  *   "staged_min_rows" see "variant"   (default 200)
  *   "staged_rows"    staged forward: query rows per work item / CTA (default 1024)
  *   "staged_persistent" staged forward A/B: 1 = one CTA per SM walking the items round-robin instead of one CTA per item

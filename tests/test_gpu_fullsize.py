@@ -1,8 +1,8 @@
 """GPU: element-wise parity at the FULL sizes of BASELINE.json's configs, through the C ABI with the
 default (auto) kernel selection -- so the shapes the bench measures are the shapes that are checked:
 
-  config 3  encoder 800x1333, Lq = S = 22223, D = 32     -> fwd_v5, bwd_v5 (fp32) / bwd_planes (bf16)
-  config 2  encoder 384x640,  Lq = S = 5100,  D = 32     -> fwd_v5, bwd_planes (three of four gradient planes fit on chip)
+  config 3  encoder 800x1333, Lq = S = 22223, D = 32     -> fwd_v5, bwd_planes
+  config 2  encoder 384x640,  Lq = S = 5100,  D = 32     -> fwd_v5, bwd_planes
   config 4  decoder Lq = 150, D = 64, S = 22223 / 5100   -> fwd_v5, bwd_v5 + msda_bwd_owned (forced here: the auto rule
             picks it for bf16 problems whose grad_value is >= 64 MB, i.e. at the bench batch sizes, not at N = 2)
 (the binned backward, the plain row backward and the staged forward, not defaults, are forced in further passes over the
@@ -59,8 +59,8 @@ FULL_SIZE = [
     # id,                 pyramid,                   Lq,   D,  expected backward kernel substring
     ("enc800x1333_d32_row", helpers.PYRAMID_800x1333, None, 32, "bwd_v5<"),
     ("enc384x640_d32_row", helpers.PYRAMID_384x640, None, 32, "bwd_v5<"),
-    ("enc800x1333_d32_auto", helpers.PYRAMID_800x1333, None, 32, "auto"),   # fp32: row kernel, bf16: planes
-    ("enc384x640_d32_auto", helpers.PYRAMID_384x640, None, 32, "bwd_planes"),  # three gradient planes fit on chip
+    ("enc800x1333_d32_auto", helpers.PYRAMID_800x1333, None, 32, "bwd_planes"),   # levels 2 + 3 on chip
+    ("enc384x640_d32_auto", helpers.PYRAMID_384x640, None, 32, "bwd_planes"),    # levels 1 - 3 on chip
     ("enc800x1333_d32_binned", helpers.PYRAMID_800x1333, None, 32, "+binned"),
     ("enc384x640_d32_binned", helpers.PYRAMID_384x640, None, 32, "+binned"),
     ("enc800x1333_d32_planes", helpers.PYRAMID_800x1333, None, 32, "bwd_planes"),
@@ -89,14 +89,15 @@ def test_full_size_elementwise_vs_oracle(lib, oracle, name, shapes, Lq, D, bsub,
     case = helpers.rounded_case(case, dtype)
     prev = lib.set_tuning("bwd_mode", 2 if name.endswith("_binned") else 4 if name.endswith("_planes") else
                           1 if name.endswith("_row") else 3 if bsub == "+owned" else 0)
-    if bsub == "auto":
-        bsub = "bwd_planes" if dtype == torch.bfloat16 else "bwd_v5<"
     prev_v = lib.set_tuning("variant", 3 if name.endswith("_row") else 0)
+    # the forced "_planes" passes use four small CTAs per SM (smallest levels on chip); auto = one 768-thread CTA per SM
+    prev_t = lib.set_tuning("planes_threads", 256 if name.endswith("_planes") else 768)
     try:
         got = run_kernels(lib, case, dtype)
     finally:
         lib.set_tuning("bwd_mode", prev)
         lib.set_tuning("variant", prev_v)
+        lib.set_tuning("planes_threads", prev_t)
     expect = "fwd_staged" if name.endswith("_row") else "fwd_v5"  # the staged forward is forced in the "_row" passes
     assert got["fwd_kernel"].startswith(expect), got["fwd_kernel"]
     assert bsub in got["bwd_kernel"], got["bwd_kernel"]

@@ -164,7 +164,8 @@ KERNEL_VARIANTS = [  # (msda_set_tuning settings, expected forward-kernel prefix
     ({"variant": 3, "v3_threads": 1024, "bwd_mode": 3}, "fwd_staged", "+owned"),
     ({"variant": 3, "v3_threads": 768, "bwd_mode": 0}, "fwd_staged", "bwd_v5"),
     ({"variant": 5, "bwd_mode": 4, "planes_rows": 64}, "fwd_v5", "bwd_planes"),
-    ({"variant": 5, "bwd_mode": 4, "planes_threads": 768, "planes_rows": 1024}, "fwd_v5", "bwd_planes"),
+    ({"variant": 5, "bwd_mode": 4, "planes_threads": 1024, "planes_budget": 20000}, "fwd_v5", "bwd_planes"),
+    ({"variant": 5, "bwd_mode": 4, "planes_threads": 256}, "fwd_v5", "bwd_planes"),
     ({"variant": 0, "staged_auto": 1, "staged_min_rows": 1, "bwd_mode": 0, "bin_min_rows": 64}, "fwd_", "bwd_v5"),
 ]
 
@@ -959,8 +960,9 @@ def test_backward_strategy_selection_for_the_baseline_configs(lib):
     S_big, S_small = 22223, 5100
     pick = lambda n, s, d, lq, dt, flags=0: raw.msda_backward_strategy(
         ctypes.byref(lib.MsdaDims(n, s, 8, d, 4, lq, 4)), lib._DTYPE_CODE[dt], flags)
-    assert pick(16, S_big, 32, S_big, torch.float32) == 1     # config 3: dense encoder -> row kernel
-    assert pick(32, S_small, 32, S_small, torch.float32) == 4  # config 2: three gradient planes fit on chip -> planes
+    assert pick(16, S_big, 32, S_big, torch.float32) == 4     # config 3: dense encoder -> planes
+    assert pick(16, S_big, 64, S_big, torch.float32) == 1     # D=64: row kernel
+    assert pick(32, S_small, 32, S_small, torch.float32) == 4  # config 2
     assert pick(32, S_big, 32, S_big, torch.bfloat16) == 4     # config 5, encoder half: dense bf16 -> planes
     assert pick(32, S_big, 32, S_big, torch.bfloat16, lib.FLAG_DETERMINISTIC) == 1
     assert pick(1, S_small, 32, 1000, torch.float32) == 1      # too few rows to fill the machine
@@ -975,3 +977,8 @@ def test_backward_strategy_selection_for_the_baseline_configs(lib):
         assert pick(16, S_big, 32, S_big, torch.float32) == 2
     finally:
         lib.set_tuning("bwd_mode", prev)
+    prev = lib.set_tuning("planes_auto", 0)
+    try:
+        assert pick(16, S_big, 32, S_big, torch.float32) == 1
+    finally:
+        lib.set_tuning("planes_auto", prev)
