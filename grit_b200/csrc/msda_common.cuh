@@ -40,6 +40,13 @@ struct Chunk<float> {
         const float4 v = *reinterpret_cast<const float4 *>(p);
         r[0] = v.x, r[1] = v.y, r[2] = v.z, r[3] = v.w;
     }
+    // streaming read of data that is dead after this use: evict-first in L1 and L2 (LDG.E.EF)
+    __device__ __forceinline__ static void load_stream(const float *p, float (&r)[4])
+    {
+        asm volatile("ld.global.cs.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3])
+                     : "l"(p));
+    }
     __device__ __forceinline__ static void store(float *p, const float (&r)[4])
     {
         *reinterpret_cast<float4 *>(p) = make_float4(r[0], r[1], r[2], r[3]);
@@ -93,6 +100,13 @@ struct ChunkBf16x4 {
     __device__ __forceinline__ static void load(const __nv_bfloat16 *p, float (&r)[4])
     {
         const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+        r[0] = __uint_as_float(v.x << 16), r[1] = __uint_as_float(v.x & 0xffff0000u);
+        r[2] = __uint_as_float(v.y << 16), r[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
+    __device__ __forceinline__ static void load_stream(const __nv_bfloat16 *p, float (&r)[4])
+    {
+        uint2 v;
+        asm volatile("ld.global.cs.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
         r[0] = __uint_as_float(v.x << 16), r[1] = __uint_as_float(v.x & 0xffff0000u);
         r[2] = __uint_as_float(v.y << 16), r[3] = __uint_as_float(v.y & 0xffff0000u);
     }
