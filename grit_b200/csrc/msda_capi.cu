@@ -557,6 +557,8 @@ int launch_bwd_planes(const msda_dims *d, const void *value, const int64_t *shap
     if (d->channels == (DD) && d->num_levels == (LL) && d->num_point == (PP))                                         \
         return th >= 1024                                                                                              \
                    ? bwd_planes_launch<T, DD, LL, PP, 1024>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st) \
+               : th >= 896                                                                                             \
+                   ? bwd_planes_launch<T, DD, LL, PP, 896>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st)  \
                : th >= 768                                                                                             \
                    ? bwd_planes_launch<T, DD, LL, PP, 768>(d, value, shapes, lsi, loc, attn, gout, gv_acc, gloc, gattn, st)  \
                : th >= 512                                                                                             \
