@@ -592,6 +592,28 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
 
+        def graph_pair(inputs, fwd_fn, bwd_fn, calls=10, replays=10):
+            """Per-call time of fwd_fn / bwd_fn when `calls` invocations are captured in one CUDA graph and replayed."""
+            res = []
+            for fn in (fwd_fn, bwd_fn):
+                fn(inputs)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for _ in range(calls):
+                        fn(inputs)
+                graph.replay()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(replays):
+                    graph.replay()
+                b.record()
+                torch.cuda.synchronize()
+                res.append(a.elapsed_time(b) / (calls * replays))
+                del graph
+            return res
+
         def time_pair(inputs, fwd_fn, bwd_fn, iters=5):
             res = []
             for fn in (fwd_fn, bwd_fn):
@@ -662,14 +684,27 @@ def main():
                 entry = {"fwd_us": f_ms * 1e3, "bwd_us_incl_alloc_zero": b_ms * 1e3,
                          "fwd_hbm_frac": fb / (f_ms * 1e-3) / 1e9 / peak, "bwd_hbm_frac": bb / (b_ms * 1e-3) / 1e9 / peak,
                          "fwd_bwd_queries_per_s": nb * c2["Lq"] / ((f_ms + b_ms) * 1e-3)}
+                # the same calls replayed from a CUDA graph: at batch 4 a call is 5-15 us of kernel behind 20-30 us of Python
+                # and launch overhead, so only the graphed figures compare KERNELS (GRIT's decoder would be graphed too)
+                gf = gb = None
+                try:
+                    gf, gb = graph_pair(x, lambda s_: _lib.forward(s_["value"], sh, ls, s_["loc"], s_["attn"]),
+                                        lambda s_: _lib.backward(s_["value"], sh, ls, s_["loc"], s_["attn"], s_["gout"]))
+                    entry.update(graphed_fwd_us=gf * 1e3, graphed_bwd_us_incl_alloc_zero=gb * 1e3)
+                except Exception as exc:
+                    entry["graphed"] = repr(exc)[:120]
                 if refmod is not None:
                     try:
-                        rf, rb = time_pair(
-                            x, lambda s_: refmod.ms_deform_attn_forward(s_["value"], sh, ls, s_["loc"], s_["attn"], 64),
-                            lambda s_: refmod.ms_deform_attn_backward(s_["value"], sh, ls, s_["loc"], s_["attn"],
-                                                                      s_["gout"], 64), iters=20)
+                        ref_f = lambda s_: refmod.ms_deform_attn_forward(s_["value"], sh, ls, s_["loc"], s_["attn"], 64)
+                        ref_b = lambda s_: refmod.ms_deform_attn_backward(s_["value"], sh, ls, s_["loc"], s_["attn"],
+                                                                          s_["gout"], 64)
+                        rf, rb = time_pair(x, ref_f, ref_b, iters=20)
                         entry.update(ref_cuda_fwd_us=rf * 1e3, ref_cuda_bwd_us=rb * 1e3,
                                      speedup_vs_ref_cuda=(rf + rb) / (f_ms + b_ms))
+                        if gf is not None:
+                            rgf, rgb = graph_pair(x, ref_f, ref_b)
+                            entry.update(ref_cuda_graphed_fwd_us=rgf * 1e3, ref_cuda_graphed_bwd_us=rgb * 1e3,
+                                         speedup_vs_ref_cuda_graphed=(rgf + rgb) / (gf + gb))
                     except Exception as exc:
                         entry["ref_cuda"] = repr(exc)[:120]
                 extras[f"{name}_N{nb}"] = entry
