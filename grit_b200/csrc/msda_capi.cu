@@ -481,6 +481,38 @@ int launch_bwd_owned(const msda_dims *d, const OwnedPlan &op, const int64_t *sha
 }
 
 // ---- coarse levels in shared-memory fixed-point planes (msda_kernels_planes.cuh) ------------------------------------
+// Query chunks per (image, head) of the planes backward for a CTA of TH threads.
+int64_t planes_chunks(const msda_dims *d, int TH)
+{
+    int rows_per_item = g_planes_rows.load();
+    if (rows_per_item <= 0) rows_per_item = TH <= 256 ? 256 : 1024;  // measured best for each CTA size
+    if (rows_per_item < 64) rows_per_item = 64;
+    int64_t chunks = (d->num_query + rows_per_item - 1) / rows_per_item;
+    if (chunks < 1) chunks = 1;
+    // One CTA per SM and items of ~130 us: when an image's item count is not a multiple of the SM count, the tail of
+    // every image runs beside the head of the next one and TWO images' value / grad_value maps compete for the L2 for most
+    // of the launch (800x1333: 176 items per image on 148 SMs -> 4.2 GB of DRAM traffic instead of 2.7 GB, 3.58 vs 3.46 ms).
+    // So the chunk count is moved, within [0.55, 1.8] x the target, to the value that fills whole waves best (37 chunks
+    // x 8 heads = 2 x 148 there).  Only when an image has at least half a wave of items; the knob "planes_rows" > 0 is
+    // taken literally.
+    if (TH > 256 && g_planes_rows.load() <= 0) {
+        const int64_t slots = device_info().sms, heads = d->num_heads;
+        if (chunks * heads * 2 >= slots) {
+            int64_t best = chunks;
+            double best_fill = 0.0;
+            const int64_t lo = (chunks * 55 + 99) / 100, hi = chunks * 18 / 10;
+            for (int64_t c = lo < 1 ? 1 : lo; c <= hi && c <= d->num_query; ++c) {
+                const int64_t n = c * heads, waves = (n + slots - 1) / slots;
+                const double fill = (double)n / (double)(waves * slots);
+                const bool closer = (c > chunks ? c - chunks : chunks - c) < (best > chunks ? best - chunks : chunks - best);
+                if (fill > best_fill + 1e-9 || (fill > best_fill - 1e-9 && closer)) best = c, best_fill = fill;
+            }
+            chunks = best;
+        }
+    }
+    return chunks;
+}
+
 template <typename T, int DD, int LL, int PP, int TH>
 int bwd_planes_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi, const void *loc,
                       const void *attn, const void *gout, float *gv_acc, void *gloc, void *gattn, cudaStream_t st)
@@ -511,38 +543,14 @@ int bwd_planes_launch(const msda_dims *d, const void *value, const int64_t *shap
         if (cap >= 0 && cap < smem) smem = (cap + 15) & ~15;
     }
     if (int rc = optin_smem(kernel, smem)) return rc;
-    int rows_per_item = g_planes_rows.load();
-    if (rows_per_item <= 0) rows_per_item = TH <= 256 ? 256 : 1024;  // measured best for each CTA size
-    if (rows_per_item < 64) rows_per_item = 64;
-    int64_t chunks = (d->num_query + rows_per_item - 1) / rows_per_item;
-    if (chunks < 1) chunks = 1;
-    // One CTA per SM and items of ~130 us: when an image's item count is not a multiple of the SM count, the tail of
-    // every image runs beside the head of the next one and TWO images' value / grad_value maps compete for the L2 for most
-    // of the launch (800x1333: 176 items per image on 148 SMs -> 4.2 GB of DRAM traffic instead of 2.7 GB, 3.58 vs 3.46 ms).
-    // So the chunk count is moved, within [0.55, 1.8] x the target, to the value that fills whole waves best (37 chunks
-    // x 8 heads = 2 x 148 there).  Only when an image has at least half a wave of items; the knob "planes_rows" > 0 is
-    // taken literally.
-    if (TH > 256 && g_planes_rows.load() <= 0) {
-        const int64_t slots = device_info().sms, heads = d->num_heads;
-        if (chunks * heads * 2 >= slots) {
-            int64_t best = chunks;
-            double best_fill = 0.0;
-            const int64_t lo = (chunks * 55 + 99) / 100, hi = chunks * 18 / 10;
-            for (int64_t c = lo < 1 ? 1 : lo; c <= hi && c <= d->num_query; ++c) {
-                const int64_t n = c * heads, waves = (n + slots - 1) / slots;
-                const double fill = (double)n / (double)(waves * slots);
-                const bool closer = (c > chunks ? c - chunks : chunks - c) < (best > chunks ? best - chunks : chunks - best);
-                if (fill > best_fill + 1e-9 || (fill > best_fill - 1e-9 && closer)) best = c, best_fill = fill;
-            }
-            chunks = best;
-        }
-    }
+    const int64_t chunks = planes_chunks(d, TH);
     const int64_t items = d->batch * chunks * d->num_heads;
     if (items > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
     kernel<<<(unsigned)items, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)loc, (const float *)attn,
                                               (const T *)gout, gv_acc, (float *)gloc, (float *)gattn, (int)d->batch,
                                               (int)d->spatial_size, (int)d->num_heads, (int)d->num_query,
-                                              (cap >= 0 && cap < smem ? cap : smem) / 4, (int)chunks);
+                                              (cap >= 0 && cap < smem ? cap : smem) / 4, (int)chunks,
+                                              (const float *)nullptr, (const float *)nullptr);
     snprintf(tl_kernel, sizeof(tl_kernel), "bwd_planes<%s,D%d,L%d,P%d,t%d>", tname<T>(), DD, LL, PP, TH);
     return MSDA_OK;
 }
@@ -1085,6 +1093,29 @@ void fused_bwd_launch(const msda_dims *d, const void *value, const int64_t *shap
              det_scale ? ",deterministic" : "");
 }
 
+// planes backward of the fused module path (D = 32 only: the auto rule's domain); one 768-thread CTA per SM
+template <typename T, int LL, int PP, int RD>
+int fused_bwd_planes_launch(const msda_dims *d, const void *value, const int64_t *shapes, const int64_t *lsi,
+                            const void *offs, const void *logits, const void *ref, const void *vratio, const void *gout,
+                            float *gv_acc, void *goffs, void *glogits, cudaStream_t st)
+{
+    constexpr int DD = 32, TH = 768;
+    using CH = typename BwdChunk<T>::type;
+    auto kernel = msda::msda_bwd_planes<T, CH, DD, LL, PP, TH, RD>;
+    const int smem = (device_info().max_smem_optin - 2048 - (TH / 32) * DD * 4) & ~15;
+    if (smem <= 0) return fail(MSDA_ERR_CUDA, "device reports no opt-in shared memory");
+    if (int rc = optin_smem(kernel, smem)) return rc;
+    const int64_t chunks = planes_chunks(d, TH);
+    const int64_t items = d->batch * chunks * d->num_heads;
+    if (items > 0x7fffffffLL) return fail(MSDA_ERR_INVALID_ARGUMENT, "grid too large");
+    kernel<<<(unsigned)items, TH, smem, st>>>((const T *)value, shapes, lsi, (const float *)offs, (const float *)logits,
+                                              (const T *)gout, gv_acc, (float *)goffs, (float *)glogits, (int)d->batch,
+                                              (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, smem / 4,
+                                              (int)chunks, (const float *)ref, (const float *)vratio);
+    snprintf(tl_kernel, sizeof(tl_kernel), "bwd_planes_fused<%s,D%d,L%d,P%d,ref%d,t%d>", tname<T>(), DD, LL, PP, RD, TH);
+    return MSDA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1162,6 +1193,24 @@ int msda_fused_backward_vr(const void *value, const int64_t *spatial_shapes, con
     if (int rc = acc_begin(dims, g, dtype, flags, grad_value, workspace, workspace_bytes, nullptr, grad_output, st,
                            &plan))
         return rc;
+    // dense D=32 problems: the planes backward (same rule as msda_backward), here with the fused point source
+    if (!plan.det && dims->channels == 32 && dims->num_levels == 4 && dims->num_point == 4 &&
+        choose_bwd_mode(dims, dtype, flags) == BWD_PLANES) {
+#define PARGS                                                                                                   \
+    dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, valid_ratios, \
+        grad_output, (float *)plan.gv_acc, grad_offsets, grad_logits, st
+        int rc = MSDA_OK;
+        if (dtype == MSDA_F32)
+            rc = ref_dim == 2 ? fused_bwd_planes_launch<float, 4, 4, 2>(PARGS) : fused_bwd_planes_launch<float, 4, 4, 4>(PARGS);
+        else
+            rc = ref_dim == 2 ? fused_bwd_planes_launch<__nv_bfloat16, 4, 4, 2>(PARGS)
+                              : fused_bwd_planes_launch<__nv_bfloat16, 4, 4, 4>(PARGS);
+#undef PARGS
+        if (rc) return rc;
+        ++tl_launches;
+        if (int rc2 = check_cuda(cudaPeekAtLastError(), "msda_fused_backward launch")) return rc2;
+        return acc_end(dims, dtype, flags, grad_value, workspace, plan, st);
+    }
 #define ARGS                                                                                                    \
     dims, value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points, valid_ratios, \
         grad_output, plan.gv_acc, plan.det_scale, grad_offsets, grad_logits, st

@@ -35,6 +35,7 @@
 #include "msda_common.cuh"
 #include "msda_kernels_staged.cuh"
 #include "msda_kernels_v5.cuh"
+#include "msda_kernels_fused.cuh"
 
 namespace msda {
 
@@ -137,12 +138,17 @@ __device__ __forceinline__ void planes_row_body(const Resolved &mine, const T *v
     }
 }
 
-template <typename T, typename CH, int D, int L, int P, int THREADS>
+// RD = 0: the plain op (loc = sampling locations, attn = attention weights, outputs grad_sampling_loc / grad_attn_weight).
+// RD = 2 | 4: the fused module path of msda_kernels_fused.cuh -- loc = raw sampling offsets, attn = attention LOGITS,
+// ref / vratio = reference points (boxes) and optional valid ratios, outputs grad_offsets / grad_logits (softmax backward
+// = one more warp reduction per row).  Softmax weights sum to 1, so the bound pre-pass needs grad_output only.
+template <typename T, typename CH, int D, int L, int P, int THREADS, int RD = 0>
 __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 1024 / THREADS : 1)  // small CTAs: several per SM, 64 registers
 msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                 const float *__restrict__ loc, const float *__restrict__ attn, const T *__restrict__ grad_out,
                 float *__restrict__ gv_acc, float *__restrict__ grad_loc, float *__restrict__ grad_attn, int N, int S,
-                int M, int Lq, int budget_words, int chunks)
+                int M, int Lq, int budget_words, int chunks, const float *__restrict__ ref = nullptr,
+                const float *__restrict__ vratio = nullptr)
 {
     constexpr int E = CH::E;
     constexpr int LPT = D / E;
@@ -167,7 +173,7 @@ msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes,
     const int MD = M * D;
     const int rp = lane % LP, rl = rp / P;
     const int rH = plan.H[rl], rW = plan.W[rl], rStart = plan.start[rl];
-    const bool r_staged = plan.sbase[rl] != kNotStaged;
+    const float rInvH = 1.f / (float)rH, rInvW = 1.f / (float)rW;  // fused path: offsets are in pixels of the level
     const unsigned plane_lane = (unsigned)__cvta_generic_to_shared(plane) + (unsigned)sub * 16u;
     unsigned rot[4];
 #pragma unroll
@@ -206,7 +212,8 @@ msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                 const int q = qb + pr;
                 const bool live = q < q1;
                 const int64_t row = ((int64_t)b * Lq + (live ? q : q0)) * M + m;
-                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(attn + row * LP) + pk);
+                float4 a4 = make_float4(0.0625f, 0.0625f, 0.0625f, 0.0625f);  // fused: a softmax, the LP weights sum to 1
+                if (RD == 0) a4 = __ldg(reinterpret_cast<const float4 *>(attn + row * LP) + pk);
                 float gq[CPL];
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
@@ -215,7 +222,7 @@ msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes,
 #pragma unroll
                     for (int e = 0; e < EV; ++e) gq[v * EV + e] = t[e];
                 }
-                float sa = (live && k_staged) ? fabsf(a4.x) + fabsf(a4.y) + fabsf(a4.z) + fabsf(a4.w) : 0.f;
+                float sa = (live && (k_staged || RD != 0)) ? fabsf(a4.x) + fabsf(a4.y) + fabsf(a4.z) + fabsf(a4.w) : 0.f;
                 sa += __shfl_xor_sync(0xffffffffu, sa, 1);
                 sa += __shfl_xor_sync(0xffffffffu, sa, 2);
 #pragma unroll
@@ -272,10 +279,16 @@ msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes,
             // row data in flight that was 2.3 GB of extra DRAM traffic per launch.
             float2 xy;
             float a_raw;
-            asm volatile("ld.global.cs.nc.v2.f32 {%0, %1}, [%2];"
-                         : "=f"(xy.x), "=f"(xy.y)
-                         : "l"(reinterpret_cast<const float2 *>(loc) + row * LP + rp));
-            asm volatile("ld.global.cs.nc.f32 %0, [%1];" : "=f"(a_raw) : "l"(attn + row * LP + rp));
+            const int64_t bq = (int64_t)b * Lq + q;
+            if (RD == 0) {
+                asm volatile("ld.global.cs.nc.v2.f32 {%0, %1}, [%2];"
+                             : "=f"(xy.x), "=f"(xy.y)
+                             : "l"(reinterpret_cast<const float2 *>(loc) + row * LP + rp));
+                asm volatile("ld.global.cs.nc.f32 %0, [%1];" : "=f"(a_raw) : "l"(attn + row * LP + rp));
+            } else {
+                fused_point<L, P, RD == 0 ? 2 : RD>(loc, attn, ref, vratio, b, row, bq, rp, rl, rInvH, rInvW, a_raw, xy.x,
+                                                    xy.y);
+            }
             const Resolved mine = resolve_point_v(xy.x, xy.y, rH, rW, rStart, a_raw);
             float go[E], gr[E];
             CH::load_stream(grad_out + row * D + sub * E, go);
@@ -290,12 +303,31 @@ msda_bwd_planes(const T *__restrict__ value, const int64_t *__restrict__ shapes,
                                             part);
             int it;
             float r3[3];
-            if (reduce_points<PPG, LPT>(part, sub, it, r3)) {
-                const int pt = it * G + g;
-                const int l = pt / P;
-                __stcs(reinterpret_cast<float2 *>(grad_loc) + row * LP + pt,
-                       make_float2((float)plan.W[l] * r3[1], (float)plan.H[l] * r3[2]));
-                __stcs(grad_attn + row * LP + pt, r3[0]);
+            const bool holder = reduce_points<PPG, LPT>(part, sub, it, r3);
+            const int pt = it * G + g;
+            const int l = pt / P;
+            if (RD == 0) {
+                if (holder) {
+                    __stcs(reinterpret_cast<float2 *>(grad_loc) + row * LP + pt,
+                           make_float2((float)plan.W[l] * r3[1], (float)plan.H[l] * r3[2]));
+                    __stcs(grad_attn + row * LP + pt, r3[0]);
+                }
+            } else {
+                // as msda_bwd_fused: the TRUE softmax weight of the point (also for skipped points), softmax backward
+                const float a_pt = __shfl_sync(0xffffffffu, a_raw, pt);
+                float dot = holder ? a_pt * r3[0] : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+                if (holder) {
+                    __stcs(grad_attn + row * LP + pt, a_pt * (r3[0] - dot));
+                    float gx = r3[1], gy = r3[2];  // 2-d: d loc / d off = 1 / (W, H) cancels the (W, H) of d(w_im, h_im) / d loc
+                    if (RD == 4) {
+                        const float4 rf = load_ref<L, RD == 0 ? 2 : RD>(ref, vratio, bq, b, l);
+                        gx = (float)plan.W[l] * gx * (rf.z * 0.5f / (float)P);
+                        gy = (float)plan.H[l] * gy * (rf.w * 0.5f / (float)P);
+                    }
+                    __stcs(reinterpret_cast<float2 *>(grad_loc) + row * LP + pt, make_float2(gx, gy));
+                }
             }
         }
 

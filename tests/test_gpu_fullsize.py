@@ -153,3 +153,43 @@ def test_fused_forward_full_size_error_vs_fp64_matches_the_unfused_path(lib, ora
     e_plain = max_norm_err(plain.double().cpu().numpy().reshape(truth.shape), truth)
     assert e_fused < 1e-5 and e_plain < 1e-5, (e_fused, e_plain)
     assert e_fused <= 2.0 * e_plain + 1e-6, (e_fused, e_plain)
+
+
+def test_module_on_a_dense_encoder_shape_takes_the_planes_backward_on_both_paths(lib):
+    """384x640 encoder shape through MSDeformAttn: big enough for the auto rule, so the fused path runs msda_bwd_planes with
+    the fused point source (softmax + location arithmetic in the kernel) and the reference-shaped path runs it with
+    materialised locations / weights; both must give the same gradients (fp32 summation order apart)."""
+    from grit_b200 import MSDeformAttn
+    from .conftest import max_norm_err
+    torch.manual_seed(11)
+    shapes_l = helpers.PYRAMID_384x640
+    N, M, D, L, P = 2, 8, 32, 4, 4
+    C, S = M * D, sum(h * w for h, w in shapes_l)
+    shapes = torch.tensor(shapes_l, device="cuda")
+    lsi = torch.from_numpy(helpers.level_start(shapes_l)).cuda()
+    mod = MSDeformAttn(C, L, M, P).cuda()
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.3 / C ** 0.5)
+        mod.attention_weights.weight.normal_(0, 1.0 / C ** 0.5)
+    query, src = torch.randn(N, S, C, device="cuda"), torch.randn(N, S, C, device="cuda")
+    ref_pts = torch.rand(N, S, L, 2, device="cuda")
+    gout = torch.randn(N, S, C, device="cuda")
+    results = {}
+    for fused in (True, False):
+        mod.fused = fused
+        mod.zero_grad(set_to_none=True)
+        q, s_ = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+        out = mod(q, ref_pts, s_, shapes, lsi, None)
+        seen = []
+
+        def note_kernel(grad):  # msda_last_kernel is thread-local: read it on the autograd thread that ran the op
+            seen.append(lib.last_kernel())
+            return grad
+        s_.register_hook(note_kernel)
+        out.backward(gout)
+        kernel = seen[0]
+        assert kernel.startswith("bwd_planes_fused" if fused else "bwd_planes<"), kernel
+        results[fused] = dict(out=out.detach(), q=q.grad, s=s_.grad, **{k: p.grad.clone() for k, p in mod.named_parameters()})
+    for k in results[True]:
+        err = max_norm_err(results[True][k].double().cpu().numpy(), results[False][k].double().cpu().numpy())
+        assert err < 2e-4, (k, err)
