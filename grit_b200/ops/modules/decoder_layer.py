@@ -119,13 +119,23 @@ def _get_clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
 
+# Hoisting the value projections saves launches, not traffic (every layer's value is written once and read once either way),
+# and the batched GEMM is no faster than six plain ones: measured on B200 (scripts/decoder_bench.py) it wins only while the
+# decoder is launch-bound -- 4.4 vs 4.6 ms at N=4, 384x640 -- and loses above that (fp32 GEMMs: 34.0 vs 32.2 ms at N=64; with
+# TF32 GEMMs 11.5 vs 5.3 ms), besides keeping n_layers values alive at once.  "auto" hoists below this many bytes of values.
+HOIST_AUTO_MAX_BYTES = 256 << 20
+
+
 def run_decoder(layers, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index, valid_ratios,
-                padding_mask=None, hoist_value_proj=True, return_intermediate=True):
+                padding_mask=None, hoist_value_proj="auto", return_intermediate=True):
     """The decoder loop of DetectionModule.forward (det_module.py:191-211) over ``layers`` with fixed reference points
     (box refinement belongs to the detection heads).  Returns (n_layers, N, Lq, C) when ``return_intermediate`` else the
-    last layer's (N, Lq, C).  ``hoist_value_proj``: one batched value_proj GEMM (+ one mask fill) for all layers."""
+    last layer's (N, Lq, C).  ``hoist_value_proj``: one batched value_proj GEMM (+ one mask fill) for all layers --
+    True, False, or "auto" (only while all the layers' values together stay below HOIST_AUTO_MAX_BYTES)."""
     values = [None] * len(layers)
     mask = padding_mask
+    if hoist_value_proj == "auto":
+        hoist_value_proj = src.numel() * src.element_size() * len(layers) <= HOIST_AUTO_MAX_BYTES
     if hoist_value_proj and len(layers) > 1:
         values = hoisted_value_proj([layer.cross_attn for layer in layers], src, padding_mask)
         mask = None  # applied once, inside hoisted_value_proj
@@ -147,7 +157,7 @@ class GraphedDecoder:
     it across calls).  Shapes are fixed at construction, as with any CUDA graph."""
 
     def __init__(self, layers, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index, valid_ratios,
-                 padding_mask=None, hoist_value_proj=True, return_intermediate=True, warmup=3):
+                 padding_mask=None, hoist_value_proj="auto", return_intermediate=True, warmup=3):
         self.layers = layers
         for layer in layers:
             layer.eval()

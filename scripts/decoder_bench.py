@@ -8,7 +8,9 @@ For every batch size it reports, for the SAME weights and inputs:
   reference_launches  the layer as the reference launches it: per-layer value_proj, softmax / location arithmetic /
                       masked_fill as separate PyTorch kernels around the sampling op, dropout + add + LayerNorm epilogues
   fused_eager         hoisted value_proj (one GEMM + one mask fill for six layers), fused sampling kernels with in-kernel
-                      valid-ratio scaling, fused residual + dropout + LayerNorm epilogues
+                      valid-ratio scaling, fused residual + dropout + LayerNorm epilogues; fused_eager_no_hoist: the same with
+                      per-layer value_proj (what hoist_value_proj="auto" picks above 256 MB of values; the training step and
+                      the graphed decoder use "auto")
   fused_graphed       the same under ONE CUDA graph (GraphedDecoder): six-layer forward latency, images/s
 and a training step (forward + backward of the six layers) for the first two.  Kernel launches per layer are counted
 with torch.profiler (CUPTI) when it is available.
@@ -61,7 +63,12 @@ def main():
     ap.add_argument("--batches", default="4,16,64")
     ap.add_argument("--d-model", type=int, default=512)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--matmul", default="fp32", choices=["fp32", "tf32"],
+                    help="precision of the layer's cuBLAS GEMMs: fp32 = torch's default, what GRIT runs (no AMP, TF32 off); "
+                         "tf32 = torch.backends.cuda.matmul.allow_tf32, a user-side switch outside this library that "
+                         "shows what the layer costs once the GEMMs stop dominating it")
     args = ap.parse_args()
+    torch.backends.cuda.matmul.allow_tf32 = args.matmul == "tf32"
     shapes_l = PYRAMIDS[args.pyramid]
     C, M, L, P, Lq, n_layers = args.d_model, 8, 4, 4, 150, 6
     S = sum(h * w for h, w in shapes_l)
@@ -76,7 +83,8 @@ def main():
             layer.cross_attn.attention_weights.weight.normal_(0, 0.2)
     shapes = torch.tensor(shapes_l, device=dev)
     lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
-    results = {"pyramid": args.pyramid, "S": S, "Lq": Lq, "d_model": C, "layers": n_layers, "gpu": torch.cuda.get_device_name(0)}
+    results = {"pyramid": args.pyramid, "S": S, "Lq": Lq, "d_model": C, "layers": n_layers, "gpu": torch.cuda.get_device_name(0),
+               "matmul": args.matmul}
 
     def configure(fused):
         for layer in layers:
@@ -112,7 +120,8 @@ def main():
         res["fused_eager"] = {"fwd_ms": timeit(lambda: fwd(True)),
                               "launches_per_layer_fwd": None if (n := count_launches(lambda: fwd(True))) is None else n / n_layers}
         res["fused_eager"]["max_err_vs_reference_launches"] = float((fwd(True) - ref_out).abs().max() / ref_out.abs().max())
-        graphed = GraphedDecoder(layers, tgt, pos, ref, src, shapes, lsi, vr, mask)
+        res["fused_eager_no_hoist"] = {"fwd_ms": timeit(lambda: fwd(False))}  # fused kernels, per-layer value_proj
+        graphed = GraphedDecoder(layers, tgt, pos, ref, src, shapes, lsi, vr, mask)  # hoist_value_proj="auto"
         ms = timeit(lambda: graphed(tgt, pos, ref, src, vr, mask))
         res["fused_graphed"] = {"fwd_ms": ms, "six_layer_latency_us": ms * 1e3, "images_per_s": N / (ms * 1e-3),
                                 "launches": 1}
@@ -121,7 +130,7 @@ def main():
         configure(False)
         res["reference_launches"]["train_step_ms"] = timeit(lambda: train_step(False), iters=10, warmup=3)
         configure(True)
-        res["fused_eager"]["train_step_ms"] = timeit(lambda: train_step(True), iters=10, warmup=3)
+        res["fused_eager"]["train_step_ms"] = timeit(lambda: train_step("auto"), iters=10, warmup=3)
         res["speedup_fwd_graphed_vs_reference_launches"] = res["reference_launches"]["fwd_ms"] / res["fused_graphed"]["fwd_ms"]
         res["speedup_train_step"] = res["reference_launches"]["train_step_ms"] / res["fused_eager"]["train_step_ms"]
         results[f"N{N}"] = res
