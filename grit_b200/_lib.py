@@ -439,12 +439,13 @@ def mask_rows_(data, mask):
 
 
 def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                  valid_ratios=None):
+                  valid_ratios=None, _validated=False):
     lib = load()
-    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                         valid_ratios=valid_ratios)
-    if why:
-        raise RuntimeError(why)
+    if not _validated:  # (True only from callers that have just run fused_supported on these very tensors)
+        why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                             valid_ratios=valid_ratios)
+        if why:
+            raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
@@ -461,12 +462,19 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
 
 
 def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                   grad_output, flags: int = 0, valid_ratios=None):
+                   grad_output, flags: int = 0, valid_ratios=None, _validated=False):
     lib = load()
-    why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
-                         grad_output=grad_output, valid_ratios=valid_ratios)
-    if why:
-        raise RuntimeError(why)
+    if _validated:  # the other tensors were checked in forward (autograd saved them): only grad_output is new
+        n, s_, m, d = value.shape
+        if not (grad_output.dtype == value.dtype and grad_output.numel() == n * sampling_offsets.shape[1] * m * d and
+                grad_output.device == value.device and grad_output.is_contiguous() and grad_output.data_ptr() % 16 == 0):
+            raise RuntimeError("grad_output must be a contiguous, 16-byte aligned tensor of value's dtype and device "
+                               "with N*Lq*M*D elements")
+    else:
+        why = _fused_problem(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits, reference_points,
+                             grad_output=grad_output, valid_ratios=valid_ratios)
+        if why:
+            raise RuntimeError(why)
     dims = fused_dims(value, sampling_offsets, reference_points)
     code = _DTYPE_CODE[value.dtype]
     grad_offs = torch.empty_like(sampling_offsets)

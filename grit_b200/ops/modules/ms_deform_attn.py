@@ -132,7 +132,7 @@ class MSDeformAttn(nn.Module):
             if _lib.fused_supported(value4, input_spatial_shapes, input_level_start_index, offs32, logits32, ref32,
                                     mask, vr32):
                 output = MSDeformAttnFusedFunction.apply(value4, input_spatial_shapes, input_level_start_index,
-                                                         offs32, logits32, ref32, mask, vr32)
+                                                         offs32, logits32, ref32, mask, vr32, True)
                 return self.output_proj(output)
             if mask is None:
                 input_padding_mask = None  # already applied above
