@@ -11,11 +11,11 @@ import sys
 from .ops.functions import (MSDeformAttnFunction, add_dropout_layer_norm, ms_deform_attn_core_pytorch,  # noqa: F401
                             pack_levels, pack_levels_groupnorm, set_deterministic)
 from .ops.modules import (DeformableTransformerDecoderLayer, GraphedDecoder, MSDeformAttn,  # noqa: F401
-                          extract_region_features, hoisted_value_proj, run_decoder)
+                          extract_region_features, graphed_training_decoder, hoisted_value_proj, run_decoder)
 
 __all__ = ["MSDeformAttn", "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "install_as_reference_ops",
            "set_deterministic", "hoisted_value_proj", "pack_levels", "pack_levels_groupnorm", "add_dropout_layer_norm",
-           "DeformableTransformerDecoderLayer", "run_decoder", "GraphedDecoder", "extract_region_features"]
+           "DeformableTransformerDecoderLayer", "graphed_training_decoder", "run_decoder", "GraphedDecoder", "extract_region_features"]
 
 
 def install_as_reference_ops(alias_models_ops: bool = True):

@@ -192,6 +192,38 @@ class GraphedDecoder:
         return self.out
 
 
+class _DecoderStack(nn.Module):
+    """``run_decoder`` as a module (what ``torch.cuda.make_graphed_callables`` wants): tensors in, tensor out."""
+
+    def __init__(self, layers, hoist_value_proj, return_intermediate):
+        super().__init__()
+        self.layers = layers if isinstance(layers, nn.ModuleList) else nn.ModuleList(layers)
+        self.kw = dict(hoist_value_proj=hoist_value_proj, return_intermediate=return_intermediate)
+
+    def forward(self, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index, valid_ratios,
+                padding_mask=None):
+        return run_decoder(self.layers, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index,
+                           valid_ratios, padding_mask, **self.kw)
+
+
+def graphed_training_decoder(layers, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index,
+                             valid_ratios, padding_mask=None, hoist_value_proj="auto", return_intermediate=True):
+    """The decoder stack for TRAINING with its forward and its backward each replayed from a CUDA graph
+    (``torch.cuda.make_graphed_callables``).  GRIT trains its detector at batch 4 per GPU (configs/detection/
+    train_config.yaml:70), where the six layers are ~900 kernel launches per step and the step is bound by the host, not by
+    the GPU; the C ABI is capture-safe and the fused autograd functions allocate through torch, so the whole stack --
+    cuBLAS GEMMs, sampling kernels, epilogues, dropout -- captures.  The arguments are sample tensors of the shapes that
+    will be used (their ``requires_grad`` flags must match the later calls); returns a callable with ``run_decoder``'s
+    positional signature.  Parameters receive ``.grad`` as usual; shapes are fixed, as with any CUDA graph."""
+    for layer in layers:
+        layer.cross_attn.validate_shapes = False  # the shape assert is a device->host sync: illegal under capture
+    stack = _DecoderStack(layers, hoist_value_proj, return_intermediate)
+    sample = (tgt, query_pos, reference_points, src, spatial_shapes, level_start_index, valid_ratios)
+    if padding_mask is not None:
+        sample = sample + (padding_mask,)
+    return torch.cuda.make_graphed_callables(stack, sample)
+
+
 def extract_region_features(layers, tgt, query_pos, reference_points, src, spatial_shapes, level_start_index,
                             valid_ratios, padding_mask=None, graphed=None):
     """Region features of a batch, the op-side pipeline of the reference's tools/extract_features.py:80-119 (batch 64,

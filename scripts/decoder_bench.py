@@ -131,6 +131,20 @@ def main():
         res["reference_launches"]["train_step_ms"] = timeit(lambda: train_step(False), iters=10, warmup=3)
         configure(True)
         res["fused_eager"]["train_step_ms"] = timeit(lambda: train_step("auto"), iters=10, warmup=3)
+        try:  # forward and backward of the stack replayed from CUDA graphs (torch.cuda.make_graphed_callables)
+            from grit_b200 import graphed_training_decoder
+            gt, gs = tgt.clone().requires_grad_(True), src.clone()
+            gfn = graphed_training_decoder(layers, gt, pos, ref, gs, shapes, lsi, vr, mask)
+
+            def graphed_step():
+                for p_ in layers.parameters():
+                    p_.grad = None
+                t = tgt.clone().requires_grad_(True)
+                gfn(t, pos, ref, src, shapes, lsi, vr, mask)[-1].sum().backward()
+            res["fused_graphed_training"] = {"fwd_ms": 0.0, "train_step_ms": timeit(graphed_step, iters=10, warmup=3)}
+            del gfn
+        except Exception as exc:  # noqa: BLE001
+            res["fused_graphed_training"] = {"fwd_ms": 0.0, "train_step_ms": 0.0, "error": repr(exc)[:200]}
         res["speedup_fwd_graphed_vs_reference_launches"] = res["reference_launches"]["fwd_ms"] / res["fused_graphed"]["fwd_ms"]
         res["speedup_train_step"] = res["reference_launches"]["train_step_ms"] / res["fused_eager"]["train_step_ms"]
         results[f"N{N}"] = res

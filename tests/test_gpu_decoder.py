@@ -228,6 +228,41 @@ def test_graphed_decoder_and_region_feature_extraction(lib):
     assert max_norm_err(feats_eager.cpu().numpy(), eager_b.cpu().numpy()) < 1e-6
 
 
+def test_graphed_training_decoder_matches_eager_gradients(lib):
+    """graphed_training_decoder: forward and backward of the decoder stack replayed from CUDA graphs (GRIT trains at batch
+    4, where the step is host-bound) == the eager stack: outputs, input gradients and parameter gradients, in eval mode
+    (no dropout) so both are deterministic functions of the inputs; then a replay with new inputs follows the inputs."""
+    import copy
+
+    from grit_b200 import graphed_training_decoder, run_decoder
+    layers, a, shapes, lsi = _decoder_problem(n_layers=3)
+    for layer in layers:
+        layer.eval()
+    eager_layers = copy.deepcopy(layers)
+
+    def step(fn, owner, tgt, src):
+        for p_ in owner.parameters():
+            p_.grad = None
+        t, s_ = tgt.clone().requires_grad_(True), src.clone().requires_grad_(True)
+        out = fn(t, a["query_pos"], a["reference_points"], s_, shapes, lsi, a["valid_ratios"], a["padding_mask"])
+        out[-1].square().sum().backward()
+        return out.detach().clone(), t.grad.clone(), s_.grad.clone(), [p_.grad.clone() for p_ in owner.parameters()]
+
+    sample_t, sample_s = a["tgt"].clone().requires_grad_(True), a["src"].clone().requires_grad_(True)
+    graphed = graphed_training_decoder(layers, sample_t, a["query_pos"], a["reference_points"], sample_s, shapes, lsi,
+                                       a["valid_ratios"], a["padding_mask"])
+    eager = lambda *args: run_decoder(eager_layers, *args)
+    for scale in (1.0, 0.5):  # second pass: new inputs through the same graphs
+        tgt, src = a["tgt"] * scale, a["src"] * scale + 0.1
+        got = step(graphed, layers, tgt, src)
+        ref = step(eager, eager_layers, tgt, src)
+        assert max_norm_err(got[0].cpu().numpy(), ref[0].cpu().numpy()) < 1e-5
+        assert max_norm_err(got[1].cpu().numpy(), ref[1].cpu().numpy()) < 2e-4
+        assert max_norm_err(got[2].cpu().numpy(), ref[2].cpu().numpy()) < 2e-4
+        for g_, r_ in zip(got[3], ref[3]):
+            assert max_norm_err(g_.cpu().numpy(), r_.cpu().numpy()) < 5e-4
+
+
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C,shapes_l", [(256, [(12, 20), (6, 10), (3, 5), (2, 3)]), (512, [(13, 21), (7, 11), (4, 6), (2, 3)])])
 def test_groupnorm_epilogue_writes_packed_memory(lib, out_dtype, C, shapes_l):
