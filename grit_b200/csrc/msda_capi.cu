@@ -78,6 +78,7 @@ constexpr int kWarps = 8;
 std::atomic<int> g_variant{0};        // forward: 0 = auto (default) | 5 = lean row kernel | 3 = persistent shared-memory-staged
 std::atomic<int> g_v3_threads{1024};  // staged forward CTA size: 512, 768 or 1024
 std::atomic<int> g_warps{4};          // row kernels, warps per CTA for D=32 L=P=4: 4 or 8
+std::atomic<int> g_bf16_x4{1};        // row forward, bf16 D=32 L=P=4: 8-byte lane chunks (0 = 16-byte chunks, the A/B alternative)
 std::atomic<int> g_hoist{0};          // row forward: issue all tap loads of a row before consuming any
 std::atomic<int> g_bwd_mode{0};       // backward: 0 auto | 1 row kernel only | 2 row + binned coarse levels | 3 owned (sparse)
                                       //           | 4 planes (coarse levels in shared-memory int32 fixed point)
@@ -187,12 +188,21 @@ void fwd_v5_launch(const msda_dims *d, const void *value, const int64_t *shapes,
                 (int)d->spatial_size, (int)d->num_heads, rpi);
         }
     }
-    if (!hoist)
+    // bf16 at D=32: 8-byte lane chunks give the kernel the fp32 kernel's shape (8 lanes per tap, 4 taps per load instruction)
+    bool x4 = false;
+    if constexpr (kFlagship && W == 4 && sizeof(T) == 2) x4 = !hoist && g_bf16_x4.load() != 0;
+    if constexpr (kFlagship && W == 4 && sizeof(T) == 2) {
+        if (x4)
+            msda::msda_fwd_v5<T, DD, LL, PP, W, false, msda::ChunkBf16x4><<<grid, W * 32, 0, st>>>(
+                (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out,
+                (int)d->spatial_size, (int)d->num_heads, rpi);
+    }
+    if (!hoist && !x4)
         msda::msda_fwd_v5<T, DD, LL, PP, W, false><<<grid, W * 32, 0, st>>>(
             (const T *)value, shapes, lsi, (const float *)loc, (const float *)attn, (T *)out, (int)d->spatial_size,
             (int)d->num_heads, rpi);
-    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v5<%s,D%d,L%d,P%d,w%d%s>", tname<T>(), DD, LL, PP, W,
-             hoist ? ",hoisted" : "");
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_v5<%s,D%d,L%d,P%d,w%d%s%s>", tname<T>(), DD, LL, PP, W,
+             hoist ? ",hoisted" : "", x4 ? ",x4" : "");
 }
 
 template <typename T>
@@ -630,6 +640,7 @@ int msda_set_tuning(const char *key, int value)
     if (key && !strcmp(key, "warps")) knob = &g_warps;
     if (key && !strcmp(key, "v3_threads")) knob = &g_v3_threads;
     if (key && !strcmp(key, "hoist")) knob = &g_hoist;
+    if (key && !strcmp(key, "bf16_x4")) knob = &g_bf16_x4;
     if (key && !strcmp(key, "bwd_mode")) knob = &g_bwd_mode;
     if (key && !strcmp(key, "bin_min_rows")) knob = &g_bin_min_rows;
     if (key && !strcmp(key, "staged_min_rows")) knob = &g_staged_min_rows;
@@ -1063,10 +1074,20 @@ void fused_fwd_launch(const msda_dims *d, const void *value, const int64_t *shap
     constexpr int W = 4;
     const unsigned rpi = (unsigned)(d->num_query * d->num_heads);
     const dim3 grid((rpi + W - 1) / W, (unsigned)d->batch);
-    msda::msda_fwd_fused<T, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
-        (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
-        (const float *)vratio, (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
-    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_fused<%s,D%d,L%d,P%d,ref%d>", tname<T>(), DD, LL, PP, RD);
+    bool x4 = false;
+    if constexpr (sizeof(T) == 2 && DD == 32) x4 = g_bf16_x4.load() != 0;  // 8-byte lane chunks, as in fwd_v5_launch
+    if constexpr (sizeof(T) == 2 && DD == 32) {
+        if (x4)
+            msda::msda_fwd_fused<T, DD, LL, PP, W, RD, msda::ChunkBf16x4><<<grid, W * 32, 0, st>>>(
+                (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
+                (const float *)vratio, (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
+    }
+    if (!x4)
+        msda::msda_fwd_fused<T, DD, LL, PP, W, RD><<<grid, W * 32, 0, st>>>(
+            (const T *)value, shapes, lsi, (const float *)offs, (const float *)logits, (const float *)ref,
+            (const float *)vratio, (T *)out, (int)d->spatial_size, (int)d->num_heads, (int)d->num_query, rpi);
+    snprintf(tl_kernel, sizeof(tl_kernel), "fwd_fused<%s,D%d,L%d,P%d,ref%d%s>", tname<T>(), DD, LL, PP, RD,
+             x4 ? ",x4" : "");
 }
 
 template <typename T, int DD, int LL, int PP, int RD>

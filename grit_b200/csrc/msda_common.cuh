@@ -103,6 +103,12 @@ struct ChunkBf16x4 {
         r[0] = __uint_as_float(v.x << 16), r[1] = __uint_as_float(v.x & 0xffff0000u);
         r[2] = __uint_as_float(v.y << 16), r[3] = __uint_as_float(v.y & 0xffff0000u);
     }
+    __device__ __forceinline__ static void store(__nv_bfloat16 *p, const float (&r)[4])
+    {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(r[0], r[1]), hi = __floats2bfloat162_rn(r[2], r[3]);
+        *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const unsigned *>(&lo),
+                                                   *reinterpret_cast<const unsigned *>(&hi));
+    }
     __device__ __forceinline__ static void load_stream(const __nv_bfloat16 *p, float (&r)[4])
     {
         uint2 v;

@@ -112,13 +112,13 @@ __device__ __forceinline__ void stage_levels_inv(const int64_t *shapes, const in
     __syncthreads();
 }
 
-template <typename T, int D, int L, int P, int WARPS, int RD>
-__global__ void __launch_bounds__(WARPS * 32, (sizeof(T) == 2 ? 1280 : 1536) / (WARPS * 32))  // as msda_fwd_v5
+template <typename T, int D, int L, int P, int WARPS, int RD, typename CH = Chunk<T>>
+__global__ void __launch_bounds__(WARPS * 32, ((sizeof(T) == 2 && CH::E == 8) ? 1280 : 1536) / (WARPS * 32))  // as msda_fwd_v5
 msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
                const float *__restrict__ offs, const float *__restrict__ logits, const float *__restrict__ ref,
                const float *__restrict__ vratio, T *__restrict__ out, int S, int M, int Lq, unsigned rows_per_image)
 {
-    constexpr int E = Chunk<T>::E;
+    constexpr int E = CH::E;
     constexpr int LPT = D / E;
     constexpr int G = 32 / LPT;
     constexpr int LP = L * P;
@@ -150,15 +150,15 @@ msda_fwd_fused(const T *__restrict__ value, const int64_t *__restrict__ shapes, 
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
     if (__all_sync(0xffffffffu, (mine.pm & 15) == 15))
-        fwd_row_body<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+        fwd_row_body<T, D, L, P, true, CH>(mine, vimg, MD, sW, g, acc);
     else
-        fwd_row_body<T, D, L, P, false>(mine, vimg, MD, sW, g, acc);
+        fwd_row_body<T, D, L, P, false, CH>(mine, vimg, MD, sW, g, acc);
 #pragma unroll
     for (int off = LPT; off < 32; off <<= 1) {
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
     }
-    if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+    if (g == 0) CH::store(out + row * D + sub * E, acc);
 }
 
 template <typename T, typename CH, typename ACC, int D, int L, int P, int WARPS, int RD>

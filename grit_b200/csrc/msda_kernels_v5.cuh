@@ -109,11 +109,11 @@ __device__ __forceinline__ void load_taps(const T *vimg, int o0, int o1, int o2,
 // (Choosing the fast path per ITERATION by a warp vote inside the general body -- 94 / 88 / 77 / 60 % of the iterations
 //  of levels 0..3 qualify with uniform locations, against 38 % of whole rows -- was measured slower: 48 instead of 40
 //  registers, 10 instead of 12 CTAs per SM, 1.43 vs 1.31 ms.)
-template <typename T, int D, int L, int P, bool ALL>
+template <typename T, int D, int L, int P, bool ALL, typename CH = Chunk<T>>
 __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg, int MD, const int (&sW)[L], int g,
-                                             float (&acc)[Chunk<T>::E])
+                                             float (&acc)[CH::E])
 {
-    constexpr int E = Chunk<T>::E;
+    constexpr int E = CH::E;
     constexpr int G = 32 / (D / E);
     constexpr int PPG = L * P / G;
 #pragma unroll
@@ -129,7 +129,7 @@ __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg
         const float w0 = ah * hw, w1 = ah * lw, w2 = al * hw, w3 = al * lw;
         if (ALL) {
             float v0[E], v1[E], v2[E], v3[E];
-            load_taps<T, Chunk<T>, true>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
+            load_taps<T, CH, true>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
 #pragma unroll
             for (int e = 0; e < E; ++e)
                 acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
@@ -144,23 +144,23 @@ __device__ __forceinline__ void fwd_row_body(const Resolved &mine, const T *vimg
             // (inline PTX) followed by predicated unpack + FMA blocks 2.81 ms.
             if constexpr (E > 4) {
                 float v0[E], v1[E], v2[E], v3[E];
-                load_taps<T, Chunk<T>, false>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
+                load_taps<T, CH, false>(vimg, o0, o1, o2, o3, pm, v0, v1, v2, v3);
 #pragma unroll
                 for (int e = 0; e < E; ++e)
                     acc[e] = fmaf(w0, v0[e], fmaf(w1, v1[e], fmaf(w2, v2[e], fmaf(w3, v3[e], acc[e]))));
                 continue;
             }
             {
-                if (pm & 8) { float v[E]; Chunk<T>::load(vimg + o3, v);
+                if (pm & 8) { float v[E]; CH::load(vimg + o3, v);
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = fmaf(w3, v[e], acc[e]); }
-                if (pm & 4) { float v[E]; Chunk<T>::load(vimg + o2, v);
+                if (pm & 4) { float v[E]; CH::load(vimg + o2, v);
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = fmaf(w2, v[e], acc[e]); }
-                if (pm & 2) { float v[E]; Chunk<T>::load(vimg + o1, v);
+                if (pm & 2) { float v[E]; CH::load(vimg + o1, v);
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = fmaf(w1, v[e], acc[e]); }
-                if (pm & 1) { float v[E]; Chunk<T>::load(vimg + o0, v);
+                if (pm & 1) { float v[E]; CH::load(vimg + o0, v);
 #pragma unroll
                     for (int e = 0; e < E; ++e) acc[e] = fmaf(w0, v[e], acc[e]); }
             }
@@ -217,13 +217,16 @@ __device__ __forceinline__ void fwd_row_body_hoisted(const Resolved &mine, const
 
 // (40 registers, 12 CTAs per SM.  A 32-register build -- __launch_bounds__(128, 16), 64 resident warps -- spills and
 //  measured 1.38 vs 1.31 ms; naming a minimum of ONE CTA per SM makes ptxas spend 92 registers and costs 35 %.)
-template <typename T, int D, int L, int P, int WARPS, bool HOIST = false>
-__global__ void __launch_bounds__(WARPS * 32, (HOIST ? 1024 : sizeof(T) == 2 ? 1280 : 1536) / (WARPS * 32))  // fp32 <= 40 registers (48 resident warps), bf16 <= 48 (40 warps)
+// CH: the lane chunk.  Chunk<T> = 16 bytes per lane (default); ChunkBf16x4 = 8 bytes (4 bf16 channels) per lane, which at
+// D=32 gives bf16 the fp32 kernel's shape -- 8 lanes per tap, 4 taps per load instruction, 4-channel register blocks, the
+// 40-register budget and the predicated-block general path -- instead of 4 lanes per tap with 8-channel blocks.
+template <typename T, int D, int L, int P, int WARPS, bool HOIST = false, typename CH = Chunk<T>>
+__global__ void __launch_bounds__(WARPS * 32, (HOIST ? 1024 : (sizeof(T) == 2 && CH::E == 8) ? 1280 : 1536) / (WARPS * 32))  // fp32 <= 40 registers (48 resident warps), bf16 <= 48 (40 warps)
 msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, const int64_t *__restrict__ lsi,
             const float *__restrict__ loc, const float *__restrict__ attn, T *__restrict__ out, int S, int M,
             unsigned rows_per_image)
 {
-    constexpr int E = Chunk<T>::E;
+    constexpr int E = CH::E;
     constexpr int LPT = D / E;
     constexpr int G = 32 / LPT;
     constexpr int LP = L * P;
@@ -250,12 +253,12 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
 #pragma unroll
     for (int e = 0; e < E; ++e) acc[e] = 0.f;
     if (__all_sync(0xffffffffu, (mine.pm & 15) == 15)) {
-        if (HOIST)
-            fwd_row_body_hoisted<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+        if constexpr (HOIST)
+            fwd_row_body_hoisted<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);  // (default chunk only)
         else
-            fwd_row_body<T, D, L, P, true>(mine, vimg, MD, sW, g, acc);
+            fwd_row_body<T, D, L, P, true, CH>(mine, vimg, MD, sW, g, acc);
     } else {
-        fwd_row_body<T, D, L, P, false>(mine, vimg, MD, sW, g, acc);
+        fwd_row_body<T, D, L, P, false, CH>(mine, vimg, MD, sW, g, acc);
     }
 
 #pragma unroll
@@ -263,7 +266,7 @@ msda_fwd_v5(const T *__restrict__ value, const int64_t *__restrict__ shapes, con
 #pragma unroll
         for (int e = 0; e < E; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
     }
-    if (g == 0) Chunk<T>::store(out + row * D + sub * E, acc);
+    if (g == 0) CH::store(out + row * D + sub * E, acc);
 }
 
 template <typename T, typename CH, typename ACC, int D, int L, int P, bool ALL, bool SKIP = false>

@@ -98,6 +98,8 @@ int64_t msda_launch_count(int reset);
  *                    3 shared-memory-staged forward
  *   "staged_auto"    0 (default) | 1: see "variant" (the row kernel measured faster on every shape since round 2)
  *   "hoist"          0 | 1   (row forward: issue all tap loads of a row before the first FMA; D=32 L=P=4 only)
+ *   "bf16_x4"        1 (default) | 0   (bf16 forward kernels at D=32 L=P=4: 8-byte lane chunks = the fp32 kernels' shape,
+ *                    2.58 vs 2.68 ms at 800x1333 N=32; 0 = 16-byte chunks)
  *   "warps"          4 | 8   (row kernels: warps per CTA; D=32 L=P=4 only)
  *   "v3_threads"     512 | 768 | 1024   (staged forward CTA size)
  *   "bwd_mode"       backward strategy: 0 auto (default) | 1 row kernel only (every tap is a global vector red) |
