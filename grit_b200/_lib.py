@@ -203,6 +203,35 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def _device_ctx(device):
+    """`torch.cuda.device(device)` only when `device` is not already current: the context manager and
+    `torch.cuda.current_stream()` (which builds a Stream object) were ~25 us of host time per library call, a tenth of
+    GRIT's batch-4 decoder step (scripts/host_overhead_profile.py)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(device)
+
+
+def _raw_stream():
+    """cudaStream_t of torch's current stream on the current device, as an integer."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:  # very old / future torch without the private accessor
+        return _raw_stream()
+
+
 _warned_generic = set()
 
 
@@ -228,8 +257,8 @@ def forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
     dims = _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
-    with torch.cuda.device(value.device), _nvtx_range("msda_forward"):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _device_ctx(value.device), _nvtx_range("msda_forward"):
+        stream = _raw_stream()
         rc = lib.msda_forward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
                               _ptr(attn_weight), _ptr(out), ctypes.byref(dims), _DTYPE_CODE[value.dtype], flags,
                               ctypes.c_void_p(stream))
@@ -255,8 +284,8 @@ def backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight
     aligned = all(t.data_ptr() % 16 == 0 for t in (value, sampling_loc, attn_weight, grad_output, grad_value, grad_loc))
     ws_bytes = lib.msda_backward_workspace_bytes(ctypes.byref(dims), code, flags | (FLAG_ALIGNED16 if aligned else 0))
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device), _nvtx_range("msda_backward"):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _device_ctx(value.device), _nvtx_range("msda_backward"):
+        stream = _raw_stream()
         rc = lib.msda_backward(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index), _ptr(sampling_loc),
                                _ptr(attn_weight), _ptr(grad_output), _ptr(grad_value), _ptr(grad_loc),
                                _ptr(grad_attn), ctypes.byref(dims), code, flags,
@@ -284,9 +313,9 @@ def pack_levels(levels, memory=None, unpack: bool = False):
         raise RuntimeError("memory must be a contiguous (N, S, C) tensor of the levels' dtype")
     ptrs = (ctypes.c_void_p * len(levels))(*[t.data_ptr() for t in levels])
     hws = (ctypes.c_int64 * len(levels))(*hw)
-    with torch.cuda.device(memory.device):
+    with _device_ctx(memory.device):
         rc = lib.msda_pack_levels(ptrs, hws, len(levels), n, c, _ptr(memory), _DTYPE_CODE[memory.dtype],
-                                  1 if unpack else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                  1 if unpack else 0, ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_pack_levels")
     return memory
@@ -311,10 +340,10 @@ def pack_levels_groupnorm(levels, weights, biases, num_groups, eps, out_dtype=to
     stats = torch.empty((len(levels), n, num_groups, 2), dtype=torch.float32, device=levels[0].device)
     arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
     hws = (ctypes.c_int64 * len(levels))(*hw)
-    with torch.cuda.device(memory.device):
+    with _device_ctx(memory.device):
         rc = lib.msda_pack_levels_groupnorm(arr(levels), hws, len(levels), n, c, int(num_groups), arr(weights),
                                             arr(biases), float(eps), _ptr(memory), _DTYPE_CODE[out_dtype], _ptr(stats),
-                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                            ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_pack_levels_groupnorm")
     return memory, stats
@@ -327,8 +356,8 @@ def probe_ceiling(which: str, scratch, iters: int = 5):
     code = {"gather": 0, "red": 1}[which]
     lines = ctypes.c_int64(0)
     best = None
-    with torch.cuda.device(scratch.device):
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    with _device_ctx(scratch.device):
+        st = ctypes.c_void_p(_raw_stream())
         for i in range(iters + 1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -430,9 +459,9 @@ def mask_rows_(data, mask):
             mask.device == data.device and tuple(data.shape[:mask.dim()]) == tuple(mask.shape)):
         raise RuntimeError("mask_rows_ expects contiguous CUDA data (..., R) and a contiguous bool mask (...) on the "
                            "same device")
-    with torch.cuda.device(data.device):
+    with _device_ctx(data.device):
         rc = lib.msda_mask_rows(_ptr(data), _ptr(mask), mask.numel(), row_bytes,
-                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_mask_rows")
     return data
@@ -449,13 +478,13 @@ def fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, at
     dims = fused_dims(value, sampling_offsets, reference_points)
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype,
                       device=value.device)
-    with torch.cuda.device(value.device), _nvtx_range("msda_fused_forward"):
+    with _device_ctx(value.device), _nvtx_range("msda_fused_forward"):
         rc = lib.msda_fused_forward_vr(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
                                        _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
                                        _ptr(valid_ratios) if valid_ratios is not None else None,
                                        int(reference_points.shape[-1]), _ptr(out), ctypes.byref(dims),
                                        _DTYPE_CODE[value.dtype], 0,
-                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                       ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_fused_forward")
     return out
@@ -486,14 +515,14 @@ def fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, a
     else:
         grad_value = torch.zeros_like(value)
     workspace = torch.empty((ws_bytes + 3) // 4, dtype=torch.float32, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device), _nvtx_range("msda_fused_backward"):
+    with _device_ctx(value.device), _nvtx_range("msda_fused_backward"):
         rc = lib.msda_fused_backward_vr(_ptr(value), _ptr(spatial_shapes), _ptr(level_start_index),
                                      _ptr(sampling_offsets), _ptr(attn_logits), _ptr(reference_points),
                                      _ptr(valid_ratios) if valid_ratios is not None else None,
                                      int(reference_points.shape[-1]), _ptr(grad_output), _ptr(grad_value),
                                      _ptr(grad_offs), _ptr(grad_logits), ctypes.byref(dims), code, flags,
                                      _ptr(workspace) if workspace is not None else None, ws_bytes,
-                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                     ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_fused_backward")
     return grad_value, grad_offs, grad_logits
@@ -526,10 +555,10 @@ def add_dropout_ln_forward(x, z, keep, keep_scale, weight, bias, eps, save_for_b
     mean = torch.empty(rows, dtype=torch.float32, device=x.device) if save_for_backward else None
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if save_for_backward else None
     opt = lambda t: _ptr(t) if t is not None else None
-    with torch.cuda.device(x.device), _nvtx_range("msda_add_dropout_ln_forward"):
+    with _device_ctx(x.device), _nvtx_range("msda_add_dropout_ln_forward"):
         rc = lib.msda_add_dropout_ln_forward(_ptr(x), _ptr(z), opt(keep), float(keep_scale), _ptr(weight), _ptr(bias),
                                              float(eps), _ptr(y), opt(h), opt(mean), opt(rstd), rows, c,
-                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                             ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_add_dropout_ln_forward")
     return y, h, mean, rstd
@@ -544,12 +573,12 @@ def add_dropout_ln_backward(grad_y, h, mean, rstd, keep, keep_scale, weight):
     grad_w, grad_b = torch.empty_like(weight), torch.empty_like(weight)
     ws_bytes = lib.msda_add_dropout_ln_workspace_bytes(rows, c)
     ws = torch.empty(max(ws_bytes // 4, 4), dtype=torch.float32, device=h.device)
-    with torch.cuda.device(h.device), _nvtx_range("msda_add_dropout_ln_backward"):
+    with _device_ctx(h.device), _nvtx_range("msda_add_dropout_ln_backward"):
         rc = lib.msda_add_dropout_ln_backward(_ptr(grad_y), _ptr(h), _ptr(mean), _ptr(rstd),
                                               _ptr(keep) if keep is not None else None, float(keep_scale),
                                               _ptr(weight), _ptr(grad_x), _ptr(grad_z), _ptr(grad_w), _ptr(grad_b),
                                               _ptr(ws), ws_bytes, rows, c,
-                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                              ctypes.c_void_p(_raw_stream()))
     if rc:
         _raise(lib, rc, "msda_add_dropout_ln_backward")
     return grad_x, grad_z, grad_w, grad_b
