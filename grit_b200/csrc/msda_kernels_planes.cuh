@@ -9,20 +9,26 @@
 // GPU -- twice the 50 G lines/s of the global reds, and on the shared-memory path, not on the XBAR path
 // (scripts/micro/smem_accumulate.cu, profiles/r02_micro_smem_accumulate.txt).  So:
 //
-//   * a work item is (image, head, chunk of ~1024 queries), one 1024-thread CTA per item (items are ordinary CTAs of a
-//     grid many times the machine, handed out by the hardware block scheduler, as in msda_kernels_staged.cuh);
+//   * a work item is (image, head, chunk of the queries), one CTA per item (items are ordinary CTAs of a grid many times
+//     the machine, handed out by the hardware block scheduler, as in msda_kernels_staged.cuh).  Default launch shape: one
+//     768-thread CTA per SM with all the shared memory, and a chunk count chosen by the host so that an image's items
+//     fill whole waves (800x1333: 37 chunks x 8 heads = 2 x 148 items of 601 queries) -- otherwise the tail of every image
+//     runs beside the head of the next and two images' value / grad_value maps compete for the L2 (4.2 instead of 2.7 GB
+//     of DRAM traffic).  Alternative ("planes_threads" 256): four 256-thread CTAs per SM, each with the smallest levels'
+//     planes in a right-sized slice of the shared memory -- faster timed alone, hungrier inside a long step;
 //   * the CTA keeps the gradient planes of the levels that fit (chosen on the device, smallest first) in shared memory
 //     as int32 fixed point.  The scale 2^k is chosen PER ITEM from a rigorous bound: a row r adds at most
 //     s_r * |g_rc| to any one (pixel, channel) of the planes, where s_r is the sum of |attention weight| over the row's
 //     points on the staged levels, so no sampling pattern can make a sum exceed W = max_c sum_r s_r |g_rc|; k is the
 //     largest integer with W * 2^k < 2^30, which leaves a factor 2 for the roundings.  The bound is computed by a
-//     pre-pass over the item's attention weights and grad_output rows (which also pulls them into L2 for the main
-//     pass).  The quantum is ~W * 2^-30: the rounding noise of a contribution is below the last bit of an fp32 add
+//     vectorised pre-pass over the item's attention weights and grad_output rows (the fused variant, RD != 0, knows the
+//     weights are a softmax and reads grad_output only).  The quantum is ~W * 2^-30: the rounding noise of a contribution is below the last bit of an fp32 add
 //     into a sum of typical size;
 //   * the rows are then walked exactly like the row kernel (warp per row, resolve once, lane group per tap, value taps
 //     from L2, grad_loc / grad_attn by shuffle reductions); taps on staged levels are 16 ATOMS.ADD per lane and
 //     iteration (4 taps x 4 channels; lane group g issues its channels rotated by g so that the four groups of a
-//     warp instruction hit disjoint banks), taps on the other levels leave as REDG like before;
+//     warp instruction hit disjoint banks), taps on the other levels leave as REDG like before; the all-taps-valid fast
+//     path is voted per ITERATION; the row's inputs and outputs are streaming (evict-first) accesses;
 //   * the planes are flushed with one vector red per non-zero 16-byte chunk: a coarse pixel crosses the XBAR once per
 //     item instead of once per tap (1 323 lines per ~32 K taps).
 //   * a non-finite bound (NaN / Inf in grad_output or in an attention weight) switches the item to reds for every
