@@ -115,3 +115,16 @@ def test_debug_core_pytorch_matches_golden():
                                                     torch.from_numpy(g["loc"]).double(),
                                                     torch.from_numpy(g["attn"]).double())
         assert max_norm_err(out.numpy(), g["out"]) < 1e-12
+
+
+def test_every_tuning_knob_is_documented_in_the_header():
+    """msda_set_tuning's keys (grit_b200/csrc/msda_capi.cu) are part of the public surface: include/msda.h documents each."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "grit_b200", "csrc", "msda_capi.cu")).read()
+    hdr = open(os.path.join(root, "include", "msda.h")).read()
+    keys = re.findall(r'!strcmp\(key, "([a-z0-9_]+)"\)', src)
+    assert len(keys) >= 10
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, f"undocumented msda_set_tuning keys: {missing}"
