@@ -259,6 +259,41 @@ def test_aggregating_backward_accumulates_into_grad_value(lib, oracle, mode, dty
     assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref) <= TOL[dtype][1]
 
 
+@pytest.mark.parametrize("threads", [256, 768])
+def test_planes_backward_worst_case_accumulation_does_not_overflow(lib, oracle, threads):
+    """The planes backward sums the coarse levels' taps as int32 fixed point with a per-item scale chosen from a bound on
+    the largest possible sum.  Worst case for that bound: EVERY row of an item puts its whole weight (attention 0.25 on
+    each of the four level-3 points, all four at the centre of the same pixel, bilinear weight 1) on one pixel, with
+    grad_output = +1 everywhere, so the pixel's sum is the number of queries -- the bound itself.  It must come out exact
+    (no wrap-around, no saturation), and a heavy-tailed variant (one row 1e6 times larger than the rest) must stay within
+    the usual tolerance relative to the largest gradient."""
+    shapes = [(40, 60), (20, 30), (10, 15), (5, 8)]
+    N, Lq, M, D, L, P = 1, 4000, 8, 32, 4, 4
+    case = helpers.make_inputs(N, Lq, M, D, shapes, P, seed=2, dtype=np.float32)
+    case["attn"][:] = 0.0
+    case["attn"][:, :, :, 3, :] = 0.25
+    case["loc"][:, :, :, 3, :, 0] = (3 + 0.5) / 8.0
+    case["loc"][:, :, :, 3, :, 1] = (2 + 0.5) / 5.0
+    case["grad_out"][:] = 1.0
+    prev = lib.set_tuning("planes_threads", threads)
+    try:
+        got = run_backward_mode(lib, case, torch.float32, "planes")
+        assert "bwd_planes" in got["bwd_kernel"]
+        ref = oracle_results(oracle, case)
+        gv = got["grad_value"].double().cpu().numpy()
+        pix = helpers.level_start(shapes)[3] + 2 * 8 + 3
+        assert np.allclose(gv[0, pix], float(Lq), rtol=0, atol=1e-3), gv[0, pix, 0, :4]
+        assert max_norm_err(gv, ref["grad_value"]) < 1e-6
+        # heavy tail: one query's gradient is 1e6 times the others'
+        case["grad_out"][0, 7, :] = 1e6
+        case["loc"][0, 7] = 0.31  # ... and lands elsewhere
+        got = run_backward_mode(lib, case, torch.float32, "planes")
+        ref = oracle_results(oracle, case)
+        assert max_norm_err(got["grad_value"].double().cpu().numpy(), ref["grad_value"]) < 1e-4
+    finally:
+        lib.set_tuning("planes_threads", prev)
+
+
 def test_nonfinite_gradients_propagate_through_aggregating_strategies(lib):
     """0 * inf and NaN in grad_output reach grad_value as NaN under every strategy (no silent zeroing)."""
     shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
